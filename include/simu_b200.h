@@ -1,0 +1,186 @@
+/*
+ * simu_b200.h -- C ABI of the B200-native phenotype-synthesis hot path
+ * (y = Gx + e over a 2-bit packed PLINK .bed) that replaces, inside
+ * precimed/simu, the two row-by-row passes over the .bed and the scalar
+ * reductions that follow them.
+ *
+ * Reference seams this ABI sits behind (paths relative to /root/reference):
+ *   find_freq()                   src/source.cc:843-885
+ *   find_pheno()                  src/source.cc:951-1006
+ *   apply_heritability()          src/source.cc:1008-1029
+ *   apply_liability_threshold()   src/source.cc:1031-1055
+ *   PioFile/PioFiles row cursor   src/source.cc:187-361
+ *   pio_open / pio_next_row / pio_skip_row / pio_reset_row / pio_close
+ *                                 libplinkio/src/plinkio/plinkio.h:58-214
+ *   bed_read_row + unpack_snps    libplinkio/src/bed.c:91-114, :321-358
+ *
+ * Conventions (carried over from libplinkio's C ABI, plinkio/status.h:16-47):
+ * integer status returns, caller-owned output buffers, no exceptions across
+ * the boundary, one context per run and per GPU, calls made from one host
+ * thread.  There is NO CPU fallback: every entry point fails with
+ * SIMU_B200_ECUDA when no sm_100 device / driver is available.
+ *
+ * Genotype coding (libplinkio/src/bed.c:75-85): packed bit pair, low bits
+ * first inside a byte: 00 = hom A1 (code 0, two A1 copies), 10 = het (code 1),
+ * 11 = hom A2 (code 2), 01 = missing (code 3).
+ */
+#ifndef SIMU_B200_H
+#define SIMU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SIMU_B200_API __attribute__((visibility("default")))
+#else
+#define SIMU_B200_API
+#endif
+
+/* Status codes.  0..2 mirror pio_status_t (PIO_OK, PIO_END, PIO_ERROR). */
+enum simu_b200_status {
+    SIMU_B200_OK = 0,
+    SIMU_B200_END = 1,      /* fewer rows in the .bed than announced (source.cc:855-858) */
+    SIMU_B200_ERROR = 2,    /* generic / read error (bed.c:349-352) */
+    SIMU_B200_EINVAL = 3,   /* bad argument */
+    SIMU_B200_ECUDA = 4,    /* CUDA runtime / driver / device error, or no GPU */
+    SIMU_B200_ENOMEM = 5,   /* host or device allocation failed */
+    SIMU_B200_EFORMAT = 6   /* not a v1.00 SNP-major .bed (source.cc:196-200) */
+};
+
+/* find_pheno accumulation modes. */
+enum simu_b200_mode {
+    /* FP64, per-sample sum in ascending causal-SNP order, separate
+     * subtract/multiply/add: bit-identical to source.cc:986-996 on one GPU. */
+    SIMU_B200_MODE_EXACT = 0,
+    /* 4-SNP lookup tables in FP32 (entries rounded from FP64), FP32 partial
+     * sums flushed to FP64: |dy| <= 1e-5 * max|y| (tests state the bound). */
+    SIMU_B200_MODE_FAST = 1
+};
+
+typedef struct simu_b200_ctx simu_b200_ctx;
+
+/* ------------------------------------------------------------------ context */
+
+SIMU_B200_API int simu_b200_version(void);
+
+/* Number of CUDA devices; *n = 0 and SIMU_B200_ECUDA when there is none. */
+SIMU_B200_API int simu_b200_device_count(int *n);
+
+/* One context per run and GPU.  num_samples = N of the .fam
+ * (pio_num_samples, plinkio.h:133).  Fails on a device that is not sm_100. */
+SIMU_B200_API int simu_b200_open(simu_b200_ctx **ctx, int device, int64_t num_samples);
+SIMU_B200_API void simu_b200_close(simu_b200_ctx *ctx);            /* pio_close */
+
+/* Text of the last error on this context (ctx == NULL: last open error). */
+SIMU_B200_API const char *simu_b200_last_error(const simu_b200_ctx *ctx);
+
+/* Run all subsequent work on an external CUDA stream (cudaStream_t), e.g.
+ * torch's current stream; NULL restores the context's own stream. */
+SIMU_B200_API int simu_b200_set_stream(simu_b200_ctx *ctx, void *cuda_stream);
+SIMU_B200_API int simu_b200_sync(simu_b200_ctx *ctx);
+
+/* Number of kernels this context has launched so far. */
+SIMU_B200_API int64_t simu_b200_launch_count(const simu_b200_ctx *ctx);
+
+/* -------------------------------------------------------------------- panel
+ * The panel is the HBM-resident packed genotype matrix: `rows` SNP rows of
+ * row_bytes = ceil(N/4) bytes (bed_header.c:219-223) at a pitch of
+ * row_stride bytes (multiple of 128).  It replaces the FILE* + one-row
+ * read_buffer of pio_bed_file_t (plinkio/bed.h:30-56). */
+
+SIMU_B200_API int64_t simu_b200_row_bytes(int64_t num_samples);
+SIMU_B200_API int64_t simu_b200_row_stride(const simu_b200_ctx *ctx);
+SIMU_B200_API int64_t simu_b200_panel_rows(const simu_b200_ctx *ctx);
+SIMU_B200_API void *simu_b200_panel_device_ptr(const simu_b200_ctx *ctx);
+
+SIMU_B200_API int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows);
+SIMU_B200_API int simu_b200_panel_free(simu_b200_ctx *ctx);
+
+/* Copy n_rows packed rows from host memory (pitch host_stride >= row_bytes)
+ * into panel rows [dst_row, dst_row+n_rows): pinned-host chunked staging on a
+ * side stream.  Replaces the fread of bed_read_row (bed.c:343-346). */
+SIMU_B200_API int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows,
+                                           const void *host_rows, int64_t host_stride);
+
+/* Read rows of a .bed file into the panel.  file_rows (ascending row numbers
+ * inside this file, NULL = 0..n_rows-1) are the causal rows; all others are
+ * seeked past, as pio_skip_row does (bed.c:360-371).  num_loci is the .bim
+ * line count.  Validates the 3-byte header (bed_header.c:80-102): returns
+ * SIMU_B200_EFORMAT unless v1.00 SNP-major, SIMU_B200_END if the file holds
+ * fewer than num_loci rows, SIMU_B200_ERROR if it holds more
+ * (source.cc:855-858, :879-882). */
+SIMU_B200_API int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t num_loci,
+                                           const int64_t *file_rows, int64_t n_rows, int64_t dst_row);
+
+/* Fill panel rows [dst_row, dst_row+n_rows) with the synthetic panel of
+ * SURVEY.md 8(d) / DESIGN.md (global SNP rows first_row..): device-side
+ * generator, byte-identical to the host generator used by the tests. */
+SIMU_B200_API int simu_b200_panel_synth(simu_b200_ctx *ctx, uint64_t panel_seed, int64_t first_row,
+                                        int64_t n_rows, int64_t dst_row);
+
+/* Copy panel rows back to the host (tests, e2e staging of synthetic data). */
+SIMU_B200_API int simu_b200_panel_get_rows(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows,
+                                           void *host_rows, int64_t host_stride);
+
+/* ------------------------------------------- hot path, host-buffer entry points
+ * These are the calls the reference's main() makes where it calls the four
+ * functions today; all pointers are HOST pointers. */
+
+/* find_freq (source.cc:843-885) over the causal SNPs.  rows[j] = panel row of
+ * the j-th causal SNP in ascending variant order (NULL = 0..mc-1).
+ * counts: mc x 4 = genocount[0..3] (source.cc:869), freq: mc doubles with the
+ * exact expression of source.cc:874-875.  Either may be NULL. */
+SIMU_B200_API int simu_b200_find_freq(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc,
+                                      int32_t *counts, double *freq);
+
+/* find_pheno (source.cc:951-1006).  freq/effect1/effect2 have one entry per
+ * causal SNP (same order as rows); effect2/pheno2 NULL for one trait.
+ * pheno arrays (N doubles) are overwritten. */
+SIMU_B200_API int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc,
+                                       const double *freq, const double *effect1, const double *effect2,
+                                       double *pheno1, double *pheno2, int mode);
+
+/* apply_heritability (source.cc:1008-1029) with the N noise draws made by the
+ * caller's RNG.  pheno updated in place; effect (m entries, may be NULL)
+ * scaled by gen_coef on the host side of the call. */
+SIMU_B200_API int simu_b200_apply_heritability(simu_b200_ctx *ctx, float hsq, double *pheno, int64_t n,
+                                               const double *noise, double *effect, int64_t m,
+                                               double *gen_coef, double *env_coef);
+
+/* Sorted order of apply_liability_threshold (source.cc:1032-1034):
+ * index[r] = sample of rank r, ascending pheno, ties by sample index. */
+SIMU_B200_API int simu_b200_liability_order(simu_b200_ctx *ctx, const double *pheno, int64_t n,
+                                            int32_t *index);
+
+/* ------------------------------------------ hot path, device-resident variants
+ * Same operations with DEVICE pointers, asynchronous on the context stream:
+ * for callers that keep x, freq and y in HBM (multi-GPU partial sums followed
+ * by an NCCL all-reduce, bench.py's device-resident timing). */
+
+SIMU_B200_API int simu_b200_find_freq_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc,
+                                          int32_t *d_counts, double *d_freq);
+SIMU_B200_API int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc,
+                                           const double *d_freq, const double *d_effect1,
+                                           const double *d_effect2, double *d_pheno1, double *d_pheno2,
+                                           int mode);
+/* *d_out = sum(y[i]^2)  (source.cc:1011). */
+SIMU_B200_API int simu_b200_sumsq_dev(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out);
+/* gen/env from *d_sumsq exactly as source.cc:1012-1025, written to
+ * d_coef[0..1]; then y = y*gen + noise*env (source.cc:1027). */
+SIMU_B200_API int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n,
+                                             const double *d_noise, const double *d_sumsq, double *d_coef);
+SIMU_B200_API int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,
+                                                int32_t *d_index);
+
+/* Device time in milliseconds of the last find_freq / find_pheno call on this
+ * context, measured with CUDA events on the launching stream (kernels only;
+ * 0 if none).  which: 0 = find_freq, 1 = find_pheno. */
+SIMU_B200_API int simu_b200_last_kernel_ms(simu_b200_ctx *ctx, int which, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMU_B200_H */

@@ -1,0 +1,204 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+import this module; nothing under ``simu_b200/`` does.  It wraps
+
+* ``liboracle.so``           -- oracle/simu_oracle.c, the restatement of
+  /root/reference/src/source.cc:843-1055 (+ the libplinkio 2-bit decode);
+* ``_ref/libsimu_ref.so``    -- the reference's own libplinkio compiled from
+  /root/reference/libplinkio (oracle/Makefile) plus oracle/ref_harness.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """Compile liboracle.so (and _ref/ when /root/reference is present)."""
+    need = force or not os.path.exists(os.path.join(_HERE, "liboracle.so"))
+    src_t = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("simu_oracle.c", "simu_oracle.h"))
+    if not need and os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < src_t:
+        need = True
+    if need or (os.path.isdir("/root/reference/libplinkio/src")
+                and not os.path.exists(os.path.join(_HERE, "_ref", "libsimu_ref.so"))):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        build()
+        L = C.CDLL(os.path.join(_HERE, "liboracle.so"))
+        L.oracle_bed_header.argtypes = [_u8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_bed_header.restype = C.c_int
+        L.oracle_bed_row_bytes.argtypes = [C.c_size_t]
+        L.oracle_bed_row_bytes.restype = C.c_size_t
+        L.oracle_unpack_snps.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_pack_snps.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_find_freq.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                       C.c_void_p, C.c_void_p]
+        L.oracle_find_pheno.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_apply_heritability.argtypes = [C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]
+        L.oracle_apply_heritability.restype = C.c_double
+        L.oracle_liability_order.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.oracle_liability_split.argtypes = [C.c_float, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_liability_labels.argtypes = [C.c_float, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_liability_labels.restype = C.c_int
+        L.oracle_synth_rows.argtypes = [C.c_uint64, C.c_int64, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+        _LIB = L
+    return _LIB
+
+
+def ref() -> C.CDLL | None:
+    """The reference's compiled libplinkio + harness, or None if not built."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libsimu_ref.so")
+        if not os.path.exists(path):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_dims.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        R.ref_read_all.argtypes = [C.c_char_p, C.c_void_p]
+        R.ref_freq_pheno.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        R.ref_locus.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int), C.c_char_p, C.c_int,
+                                C.POINTER(C.c_longlong), C.c_char_p, C.c_char_p, C.c_int]
+        R.ref_sample.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p, C.c_int]
+        _REF = R
+    return _REF
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------- wrappers
+
+def bed_header(b: bytes):
+    v, o = C.c_int(), C.c_int()
+    off = lib().oracle_bed_header(np.frombuffer(bytes(b[:3]).ljust(3, b"\0"), dtype=np.uint8).copy(),
+                                  C.byref(v), C.byref(o))
+    return v.value, o.value, off
+
+
+def row_bytes(n: int) -> int:
+    return int(lib().oracle_bed_row_bytes(n))
+
+
+def unpack(packed: np.ndarray, n: int) -> np.ndarray:
+    packed = np.ascontiguousarray(packed, dtype=np.uint8)
+    out = np.empty(n, dtype=np.uint8)
+    lib().oracle_unpack_snps(_ptr(packed), _ptr(out), n)
+    return out
+
+
+def pack(codes: np.ndarray) -> np.ndarray:
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    out = np.empty(row_bytes(codes.size), dtype=np.uint8)
+    lib().oracle_pack_snps(_ptr(codes), _ptr(out), codes.size)
+    return out
+
+
+def find_freq(rows: np.ndarray, n: int, row_index=None):
+    """rows: [R, stride] uint8.  Returns (counts[mc,4] int32, freq[mc] f64)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    idx = None if row_index is None else np.ascontiguousarray(row_index, dtype=np.int64)
+    mc = rows.shape[0] if idx is None else idx.size
+    counts = np.zeros((mc, 4), dtype=np.int32)
+    freq = np.zeros(mc, dtype=np.float64)
+    lib().oracle_find_freq(_ptr(rows), rows.shape[1], _ptr(idx), mc, n, _ptr(counts), _ptr(freq))
+    return counts, freq
+
+
+def find_pheno(rows: np.ndarray, n: int, freq, x1, x2=None, row_index=None):
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    idx = None if row_index is None else np.ascontiguousarray(row_index, dtype=np.int64)
+    mc = rows.shape[0] if idx is None else idx.size
+    freq = np.ascontiguousarray(freq, dtype=np.float64)
+    x1 = np.ascontiguousarray(x1, dtype=np.float64)
+    x2 = None if x2 is None else np.ascontiguousarray(x2, dtype=np.float64)
+    y1 = np.zeros(n, dtype=np.float64)
+    y2 = None if x2 is None else np.zeros(n, dtype=np.float64)
+    lib().oracle_find_pheno(_ptr(rows), rows.shape[1], _ptr(idx), mc, n, _ptr(freq), _ptr(x1), _ptr(x2),
+                            _ptr(y1), _ptr(y2))
+    return y1, y2
+
+
+def apply_heritability(hsq: float, pheno: np.ndarray, noise: np.ndarray, effect: np.ndarray | None = None):
+    """In place on copies; returns (pheno, effect, gen_coef, env_coef)."""
+    pheno = np.array(pheno, dtype=np.float64)
+    noise = np.ascontiguousarray(noise, dtype=np.float64)
+    eff = None if effect is None else np.array(effect, dtype=np.float64)
+    env = C.c_double()
+    gen = lib().oracle_apply_heritability(hsq, _ptr(pheno), pheno.size, _ptr(noise), _ptr(eff),
+                                          0 if eff is None else eff.size, C.byref(env))
+    return pheno, eff, gen, env.value
+
+
+def liability_order(pheno: np.ndarray) -> np.ndarray:
+    pheno = np.ascontiguousarray(pheno, dtype=np.float64)
+    idx = np.empty(pheno.size, dtype=np.int32)
+    lib().oracle_liability_order(_ptr(pheno), pheno.size, _ptr(idx))
+    return idx
+
+
+def liability_split(k: float, n: int):
+    a, b = C.c_int(), C.c_int()
+    lib().oracle_liability_split(k, n, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def liability_labels(k, ncas, ncon, index, con_inds, cas_inds):
+    n = index.size
+    out = np.empty(n, dtype=np.float64)
+    rc = lib().oracle_liability_labels(k, ncas, ncon, n,
+                                       _ptr(np.ascontiguousarray(index, dtype=np.int32)),
+                                       _ptr(np.ascontiguousarray(con_inds, dtype=np.int32)),
+                                       _ptr(np.ascontiguousarray(cas_inds, dtype=np.int32)), _ptr(out))
+    if rc:
+        raise RuntimeError("ERROR: too many controls requested" if rc == -1 else "ERROR: too many cases requested")
+    return out
+
+
+def synth_rows(seed: int, first_row: int, n_rows: int, n: int, stride: int | None = None,
+               threads: int = 0) -> np.ndarray:
+    """Synthetic packed rows [n_rows, stride] (SURVEY.md 8d generator)."""
+    stride = stride or row_bytes(n)
+    out = np.zeros((n_rows, stride), dtype=np.uint8)
+    threads = threads or min(os.cpu_count() or 1, 16)
+    L = lib()
+    if n_rows * n < 1 << 22 or threads == 1:
+        L.oracle_synth_rows(seed, first_row, n_rows, n, _ptr(out), stride)
+        return out
+    chunk = (n_rows + threads - 1) // threads
+
+    def work(t):
+        lo, hi = t * chunk, min(n_rows, (t + 1) * chunk)
+        if lo < hi:
+            L.oracle_synth_rows(seed, first_row + lo, hi - lo, n, C.c_void_p(out.ctypes.data + lo * stride), stride)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out

@@ -1,0 +1,566 @@
+// C-ABI layer: context, HBM panel, pinned-host chunked staging, and the
+// entry points declared in include/simu_b200.h.  No torch types, no CPU
+// fallback: without a B200 every call returns SIMU_B200_ECUDA.
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <new>
+
+#include "ctx.cuh"
+
+static thread_local std::string g_open_error;
+
+int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_open_error = buf;
+    return code;
+}
+
+int ctx_cuda(simu_b200_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return SIMU_B200_OK;
+    return ctx_fail(ctx, e == cudaErrorMemoryAllocation ? SIMU_B200_ENOMEM : SIMU_B200_ECUDA,
+                    "CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+void *ctx_scratch(simu_b200_ctx *ctx, int slot, size_t bytes)
+{
+    if (bytes == 0) bytes = 256;
+    if (ctx->scratch_bytes[slot] >= bytes) return ctx->scratch[slot];
+    if (ctx->scratch[slot]) { cudaFree(ctx->scratch[slot]); ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0; }
+    size_t want = bytes + bytes / 4;   // grow with slack
+    want = (want + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+    if (e != cudaSuccess) { ctx_cuda(ctx, e, "scratch cudaMalloc"); return nullptr; }
+    ctx->scratch_bytes[slot] = want;
+    return ctx->scratch[slot];
+}
+
+// ---------------------------------------------------------------- context
+
+extern "C" {
+
+int simu_b200_version(void) { return SIMU_B200_VERSION; }
+
+int simu_b200_device_count(int *n)
+{
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (n) *n = (e == cudaSuccess) ? c : 0;
+    if (e != cudaSuccess || c == 0)
+        return ctx_fail(nullptr, SIMU_B200_ECUDA, "no CUDA device available (%s); simu_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return SIMU_B200_OK;
+}
+
+const char *simu_b200_last_error(const simu_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_open_error.c_str(); }
+
+int64_t simu_b200_row_bytes(int64_t num_samples) { return (num_samples + 3) / 4; }   // bed_header.c:219-223
+int64_t simu_b200_row_stride(const simu_b200_ctx *ctx) { return ctx ? ctx->row_stride : 0; }
+int64_t simu_b200_panel_rows(const simu_b200_ctx *ctx) { return ctx ? ctx->panel_rows : 0; }
+void *simu_b200_panel_device_ptr(const simu_b200_ctx *ctx) { return ctx ? ctx->panel : nullptr; }
+int64_t simu_b200_launch_count(const simu_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int simu_b200_open(simu_b200_ctx **out, int device, int64_t num_samples)
+{
+    if (!out) return ctx_fail(nullptr, SIMU_B200_EINVAL, "open: ctx pointer is NULL");
+    *out = nullptr;
+    if (num_samples <= 0 || num_samples > 0x7FFFFFF0ll)
+        return ctx_fail(nullptr, SIMU_B200_EINVAL, "open: num_samples %lld out of range", (long long)num_samples);
+    int n = 0;
+    int rc = simu_b200_device_count(&n);
+    if (rc != SIMU_B200_OK) return rc;
+    if (device < 0 || device >= n)
+        return ctx_fail(nullptr, SIMU_B200_EINVAL, "open: device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return ctx_cuda(nullptr, e, "cudaGetDeviceProperties");
+    if (prop.major != 10)
+        return ctx_fail(nullptr, SIMU_B200_ECUDA, "device %d (%s, sm_%d%d) is not a B200-class sm_100 GPU; "
+                        "simu_b200 ships sm_100a kernels only and has no fallback", device, prop.name, prop.major, prop.minor);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return ctx_cuda(nullptr, e, "cudaSetDevice");
+
+    simu_b200_ctx *ctx = new (std::nothrow) simu_b200_ctx();
+    if (!ctx) return ctx_fail(nullptr, SIMU_B200_ENOMEM, "open: out of host memory");
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->n_samples = num_samples;
+    ctx->row_bytes = simu_b200_row_bytes(num_samples);
+    ctx->row_stride = (ctx->row_bytes + SIMU_ROW_ALIGN - 1) / SIMU_ROW_ALIGN * SIMU_ROW_ALIGN;
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_stage[0], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_stage[1], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
+        rc = ctx_cuda(nullptr, e, "stream/event creation");
+        simu_b200_close(ctx);
+        return rc;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SIMU_B200_OK;
+}
+
+void simu_b200_close(simu_b200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->panel) cudaFree(ctx->panel);
+    for (int i = 0; i < 12; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int simu_b200_set_stream(simu_b200_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SIMU_B200_OK;
+}
+
+int simu_b200_sync(simu_b200_ctx *ctx)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_last_kernel_ms(simu_b200_ctx *ctx, int which, float *ms)
+{
+    if (!ctx || !ms || which < 0 || which > 1) return SIMU_B200_EINVAL;
+    *ms = ctx->last_ms[which];
+    return SIMU_B200_OK;
+}
+
+// ------------------------------------------------------------------ panel
+
+int simu_b200_panel_free(simu_b200_ctx *ctx)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (ctx->panel) { CUDA_TRY(ctx, cudaFree(ctx->panel)); }
+    ctx->panel = nullptr;
+    ctx->panel_rows = 0;
+    return SIMU_B200_OK;
+}
+
+int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    if (num_rows <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_alloc: num_rows must be positive");
+    int rc = simu_b200_panel_free(ctx);
+    if (rc) return rc;
+    const size_t bytes = (size_t)num_rows * (size_t)ctx->row_stride;
+    cudaError_t e = cudaMalloc((void **)&ctx->panel, bytes);
+    if (e != cudaSuccess)
+        return ctx_fail(ctx, SIMU_B200_ENOMEM, "panel_alloc: cannot allocate %zu bytes of HBM (%s)", bytes,
+                        cudaGetErrorString(e));
+    ctx->panel_rows = num_rows;
+    // pitch padding is never interpreted by the kernels (they mask to N); zero it once so that
+    // panel_get_rows and debuggers see defined bytes.
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->panel, 0, bytes, ctx->stream));
+    return SIMU_B200_OK;
+}
+
+static int ensure_pinned(simu_b200_ctx *ctx)
+{
+    for (int i = 0; i < 2; i++)
+        if (!ctx->pinned[i]) {
+            cudaError_t e = cudaHostAlloc((void **)&ctx->pinned[i], SIMU_STAGE_BYTES, cudaHostAllocDefault);
+            if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaHostAlloc(staging)");
+        }
+    return SIMU_B200_OK;
+}
+
+static int check_rows(simu_b200_ctx *ctx, const char *who, int64_t first, int64_t n)
+{
+    if (!ctx->panel) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: no panel allocated", who);
+    if (n < 0 || first < 0 || first + n > ctx->panel_rows)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: rows [%lld, %lld) outside panel of %lld rows", who,
+                        (long long)first, (long long)(first + n), (long long)ctx->panel_rows);
+    return SIMU_B200_OK;
+}
+
+// make the compute stream wait for everything queued on the copy stream
+static int join_copy_stream(simu_b200_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    return SIMU_B200_OK;
+}
+
+// make the copy stream wait for everything queued on the compute stream (panel memset etc.)
+static int fork_copy_stream(simu_b200_ctx *ctx)
+{
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows, const void *host_rows,
+                             int64_t host_stride)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = check_rows(ctx, "panel_put_rows", dst_row, n_rows);
+    if (rc) return rc;
+    if (n_rows == 0) return SIMU_B200_OK;
+    if (!host_rows || host_stride < ctx->row_bytes)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_put_rows: bad host buffer (stride %lld < row bytes %lld)",
+                        (long long)host_stride, (long long)ctx->row_bytes);
+    if ((rc = fork_copy_stream(ctx))) return rc;
+
+    cudaPointerAttributes attr;
+    bool is_pinned = (cudaPointerGetAttributes(&attr, host_rows) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    const uint8_t *src = (const uint8_t *)host_rows;
+    if (is_pinned) {
+        // already page-locked: DMA straight from the caller's buffer, in chunks so that the
+        // copy engine pipeline stays short-queued
+        const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
+        for (int64_t r = 0; r < n_rows; r += rows_per) {
+            const int64_t nr = std::min(rows_per, n_rows - r);
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->panel + (dst_row + r) * ctx->row_stride, (size_t)ctx->row_stride,
+                                            src + r * host_stride, (size_t)host_stride, (size_t)ctx->row_bytes,
+                                            (size_t)nr, cudaMemcpyHostToDevice, ctx->copy_stream));
+        }
+    } else {
+        if ((rc = ensure_pinned(ctx))) return rc;
+        const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
+        int buf = 0;
+        bool used[2] = {false, false};
+        for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1) {
+            const int64_t nr = std::min(rows_per, n_rows - r);
+            if (used[buf]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stage[buf]));
+            if (host_stride == ctx->row_bytes) {
+                memcpy(ctx->pinned[buf], src + r * host_stride, (size_t)(nr * ctx->row_bytes));
+            } else {
+                for (int64_t q = 0; q < nr; q++)
+                    memcpy(ctx->pinned[buf] + q * ctx->row_bytes, src + (r + q) * host_stride, (size_t)ctx->row_bytes);
+            }
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->panel + (dst_row + r) * ctx->row_stride, (size_t)ctx->row_stride,
+                                            ctx->pinned[buf], (size_t)ctx->row_bytes, (size_t)ctx->row_bytes,
+                                            (size_t)nr, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stage[buf], ctx->copy_stream));
+            used[buf] = true;
+        }
+    }
+    return join_copy_stream(ctx);
+}
+
+int simu_b200_panel_get_rows(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows, void *host_rows,
+                             int64_t host_stride)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = check_rows(ctx, "panel_get_rows", src_row, n_rows);
+    if (rc) return rc;
+    if (n_rows == 0) return SIMU_B200_OK;
+    if (!host_rows || host_stride < ctx->row_bytes)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_get_rows: bad host buffer");
+    // chunk so that a single 2D copy never exceeds the pitch/height limits
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(256u << 20) / ctx->row_bytes);
+    for (int64_t r = 0; r < n_rows; r += rows_per) {
+        const int64_t nr = std::min(rows_per, n_rows - r);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync((uint8_t *)host_rows + r * host_stride, (size_t)host_stride,
+                                        ctx->panel + (src_row + r) * ctx->row_stride, (size_t)ctx->row_stride,
+                                        (size_t)ctx->row_bytes, (size_t)nr, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t num_loci, const int64_t *file_rows,
+                             int64_t n_rows, int64_t dst_row)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = check_rows(ctx, "panel_load_bed", dst_row, n_rows);
+    if (rc) return rc;
+    if (!bed_path) return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_load_bed: path is NULL");
+    int fd = open(bed_path, O_RDONLY);
+    if (fd < 0) return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Could not open %s (%s)", bed_path, strerror(errno));
+    unsigned char hdr[3] = {0, 0, 0};
+    if (pread(fd, hdr, 3, 0) != 3) {                       // parse_header, bed.c:52-58
+        close(fd);
+        return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Could not open %s (file shorter than a BED header)", bed_path);
+    }
+    // bed_header.c:80-102: v1.00 magic 6c 1b, third byte 01 = one locus per row
+    if (!(hdr[0] == 0x6c && hdr[1] == 0x1b && hdr[2] == 0x01)) {
+        close(fd);
+        return ctx_fail(ctx, SIMU_B200_EFORMAT,
+                        "ERROR: Unsupported format in %s, snps must be rows, samples must be columns", bed_path);
+    }
+    if (n_rows == 0) { close(fd); return SIMU_B200_OK; }
+    if ((rc = ensure_pinned(ctx)) || (rc = fork_copy_stream(ctx))) { close(fd); return rc; }
+
+    const int64_t B = ctx->row_bytes;
+    const int64_t cap_rows = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / B);
+    int buf = 0;
+    bool used[2] = {false, false};
+    int64_t done = 0, prev = -1;
+    while (done < n_rows) {
+        const int64_t nr = std::min(cap_rows, n_rows - done);
+        if (used[buf]) {
+            cudaError_t e = cudaEventSynchronize(ctx->ev_stage[buf]);
+            if (e != cudaSuccess) { close(fd); return ctx_cuda(ctx, e, "staging event sync"); }
+        }
+        // coalesce runs of adjacent causal rows into single preads (pio_skip_row defers the
+        // seek the same way, bed.c:333-341)
+        int64_t q = 0;
+        while (q < nr) {
+            const int64_t r0 = file_rows ? file_rows[done + q] : done + q;
+            if (r0 <= prev || r0 >= num_loci) {
+                close(fd);
+                if (r0 >= num_loci)                     // source.cc:855-858
+                    return ctx_fail(ctx, SIMU_B200_END, "ERROR: expect to find %lld variants across input files; "
+                                    "row %lld requested. Are input Plink files corrupted?", (long long)num_loci, (long long)r0);
+                return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_load_bed: file_rows must be strictly ascending");
+            }
+            int64_t run = 1;
+            while (q + run < nr && (file_rows ? file_rows[done + q + run] : r0 + run) == r0 + run) run++;
+            size_t want = (size_t)(run * B), got = 0;
+            while (got < want) {
+                ssize_t k = pread(fd, ctx->pinned[buf] + q * B + got, want - got, (off_t)(3 + r0 * B + (int64_t)got));
+                if (k <= 0) {                           // short read: bed.c:349-352 -> source.cc:226-229
+                    close(fd);
+                    return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Error reading from %s", bed_path);
+                }
+                got += (size_t)k;
+            }
+            prev = r0 + run - 1;
+            q += run;
+        }
+        cudaError_t e = cudaMemcpy2DAsync(ctx->panel + (dst_row + done) * ctx->row_stride, (size_t)ctx->row_stride,
+                                          ctx->pinned[buf], (size_t)B, (size_t)B, (size_t)nr, cudaMemcpyHostToDevice,
+                                          ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_stage[buf], ctx->copy_stream);
+        if (e != cudaSuccess) { close(fd); return ctx_cuda(ctx, e, "staging copy"); }
+        used[buf] = true;
+        buf ^= 1;
+        done += nr;
+    }
+    close(fd);
+    // the staging buffers are reused by the next call: drain before returning
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return join_copy_stream(ctx);
+}
+
+int simu_b200_panel_synth(simu_b200_ctx *ctx, uint64_t panel_seed, int64_t first_row, int64_t n_rows,
+                          int64_t dst_row)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = check_rows(ctx, "panel_synth", dst_row, n_rows);
+    if (rc) return rc;
+    return launch_synth(ctx, panel_seed, first_row, n_rows, dst_row);
+}
+
+// ------------------------------------------------ device-resident variants
+
+static int check_hot(simu_b200_ctx *ctx, const char *who, int64_t mc)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    if (!ctx->panel) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: no panel allocated", who);
+    if (mc < 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: negative causal count", who);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    return ctx_cuda(ctx, e, "cudaSetDevice");
+}
+
+int simu_b200_find_freq_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts,
+                            double *d_freq)
+{
+    int rc = check_hot(ctx, "find_freq", mc);
+    if (rc) return rc;
+    if (!d_rows && mc > ctx->panel_rows)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq: %lld causal rows but panel holds %lld", (long long)mc,
+                        (long long)ctx->panel_rows);
+    return launch_counts(ctx, d_rows, mc, d_counts, d_freq);
+}
+
+int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                             const double *d_effect1, const double *d_effect2, double *d_pheno1,
+                             double *d_pheno2, int mode)
+{
+    int rc = check_hot(ctx, "find_pheno", mc);
+    if (rc) return rc;
+    if (!d_rows && mc > ctx->panel_rows)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: %lld causal rows but panel holds %lld", (long long)mc,
+                        (long long)ctx->panel_rows);
+    if (!d_freq || !d_effect1 || !d_pheno1 || ((d_effect2 == nullptr) != (d_pheno2 == nullptr)))
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: NULL argument (effect2/pheno2 must be both set or both NULL)");
+    if (mode == SIMU_B200_MODE_EXACT)
+        return launch_pheno_exact(ctx, d_rows, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
+    if (mode == SIMU_B200_MODE_FAST)
+        return launch_pheno_lut(ctx, d_rows, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
+    return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: unknown mode %d", mode);
+}
+
+int simu_b200_sumsq_dev(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return launch_sumsq(ctx, d_y, n, d_out);
+}
+
+int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
+                               const double *d_sumsq, double *d_coef)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return launch_heritability(ctx, hsq, d_y, n, d_noise, d_sumsq, d_coef);
+}
+
+int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n, int32_t *d_index)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return launch_argsort_f64(ctx, d_pheno, n, d_index);
+}
+
+// --------------------------------------------------- host-buffer entry points
+
+static int h2d(simu_b200_ctx *ctx, int slot, const void *src, size_t bytes, void **dst)
+{
+    void *d = ctx_scratch(ctx, slot, bytes);
+    if (!d) return SIMU_B200_ENOMEM;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dst = d;
+    return SIMU_B200_OK;
+}
+
+static int check_row_list(simu_b200_ctx *ctx, const char *who, const int32_t *rows, int64_t mc)
+{
+    if (!rows) {
+        if (mc > ctx->panel_rows)
+            return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: %lld causal rows but panel holds %lld", who, (long long)mc,
+                            (long long)ctx->panel_rows);
+        return SIMU_B200_OK;
+    }
+    for (int64_t j = 0; j < mc; j++)
+        if (rows[j] < 0 || rows[j] >= ctx->panel_rows)
+            return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: rows[%lld] = %d outside panel of %lld rows", who,
+                            (long long)j, rows[j], (long long)ctx->panel_rows);
+    return SIMU_B200_OK;
+}
+
+int simu_b200_find_freq(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, int32_t *counts, double *freq)
+{
+    int rc = check_hot(ctx, "find_freq", mc);
+    if (rc || (rc = check_row_list(ctx, "find_freq", rows, mc))) return rc;
+    if (mc == 0) return SIMU_B200_OK;
+    void *d_rows = nullptr;
+    if (rows && (rc = h2d(ctx, SCR_ROWS, rows, (size_t)mc * 4, &d_rows))) return rc;
+    int32_t *d_counts = (int32_t *)ctx_scratch(ctx, SCR_COUNTS, (size_t)mc * 16);
+    double *d_freq = (double *)ctx_scratch(ctx, SCR_FREQ, (size_t)mc * 8);
+    if (!d_counts || !d_freq) return SIMU_B200_ENOMEM;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    if ((rc = launch_counts(ctx, (const int32_t *)d_rows, mc, d_counts, d_freq))) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    if (counts) CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)mc * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (freq) CUDA_TRY(ctx, cudaMemcpyAsync(freq, d_freq, (size_t)mc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[0], ctx->ev_a, ctx->ev_b));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, const double *freq,
+                         const double *effect1, const double *effect2, double *pheno1, double *pheno2, int mode)
+{
+    int rc = check_hot(ctx, "find_pheno", mc);
+    if (rc || (rc = check_row_list(ctx, "find_pheno", rows, mc))) return rc;
+    if (!pheno1 || ((effect2 == nullptr) != (pheno2 == nullptr)) || (mc > 0 && (!freq || !effect1)))
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: NULL argument (effect2/pheno2 must be both set or both NULL)");
+    if (mode != SIMU_B200_MODE_EXACT && mode != SIMU_B200_MODE_FAST)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: unknown mode %d", mode);
+    const int64_t n = ctx->n_samples;
+    if (mc == 0) {                                           // source.cc:962-966: phenotypes start at 0
+        for (int64_t i = 0; i < n; i++) { pheno1[i] = 0; if (pheno2) pheno2[i] = 0; }
+        return SIMU_B200_OK;
+    }
+    void *d_rows = nullptr, *d_freq = nullptr, *d_x1 = nullptr, *d_x2 = nullptr;
+    if (rows && (rc = h2d(ctx, SCR_ROWS, rows, (size_t)mc * 4, &d_rows))) return rc;
+    if ((rc = h2d(ctx, SCR_FREQ, freq, (size_t)mc * 8, &d_freq))) return rc;
+    if ((rc = h2d(ctx, SCR_X1, effect1, (size_t)mc * 8, &d_x1))) return rc;
+    if (effect2 && (rc = h2d(ctx, SCR_X2, effect2, (size_t)mc * 8, &d_x2))) return rc;
+    double *d_y1 = (double *)ctx_scratch(ctx, SCR_Y1, (size_t)n * 8);
+    double *d_y2 = effect2 ? (double *)ctx_scratch(ctx, SCR_Y2, (size_t)n * 8) : nullptr;
+    if (!d_y1 || (effect2 && !d_y2)) return SIMU_B200_ENOMEM;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    rc = simu_b200_find_pheno_dev(ctx, (const int32_t *)d_rows, mc, (const double *)d_freq, (const double *)d_x1,
+                                  (const double *)d_x2, d_y1, d_y2, mode);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(pheno1, d_y1, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pheno2) CUDA_TRY(ctx, cudaMemcpyAsync(pheno2, d_y2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_a, ctx->ev_b));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_apply_heritability(simu_b200_ctx *ctx, float hsq, double *pheno, int64_t n, const double *noise,
+                                 double *effect, int64_t m, double *gen_coef, double *env_coef)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!pheno || !noise || n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "apply_heritability: bad arguments");
+    void *d_y = nullptr, *d_noise = nullptr;
+    int rc;
+    if ((rc = h2d(ctx, SCR_Y1, pheno, (size_t)n * 8, &d_y))) return rc;
+    if ((rc = h2d(ctx, SCR_NOISE, noise, (size_t)n * 8, &d_noise))) return rc;
+    double *d_misc = (double *)ctx_scratch(ctx, SCR_COUNTS, 64);
+    if (!d_misc) return SIMU_B200_ENOMEM;
+    if ((rc = launch_sumsq(ctx, (const double *)d_y, n, d_misc))) return rc;
+    if ((rc = launch_heritability(ctx, hsq, (double *)d_y, n, (const double *)d_noise, d_misc, d_misc + 1))) return rc;
+    double coef[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(pheno, d_y, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(coef, d_misc + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (effect) for (int64_t i = 0; i < m; i++) effect[i] *= coef[0];   // source.cc:1028
+    if (gen_coef) *gen_coef = coef[0];
+    if (env_coef) *env_coef = coef[1];
+    return SIMU_B200_OK;
+}
+
+int simu_b200_liability_order(simu_b200_ctx *ctx, const double *pheno, int64_t n, int32_t *index)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!pheno || !index || n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "liability_order: bad arguments");
+    void *d_y = nullptr;
+    int rc;
+    if ((rc = h2d(ctx, SCR_Y1, pheno, (size_t)n * 8, &d_y))) return rc;
+    int32_t *d_idx = (int32_t *)ctx_scratch(ctx, SCR_COUNTS, (size_t)n * 4);
+    if (!d_idx) return SIMU_B200_ENOMEM;
+    if ((rc = launch_argsort_f64(ctx, (const double *)d_y, n, d_idx))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(index, d_idx, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SIMU_B200_OK;
+}
+
+}  // extern "C"

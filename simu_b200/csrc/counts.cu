@@ -1,0 +1,127 @@
+// Kernel (a): per-SNP allele counts and A1 frequency.
+//
+// Replaces find_freq's inner loop (/root/reference/src/source.cc:869-875) and
+// the bed_read_row + unpack_snps it sits on (libplinkio/src/bed.c:91-114,
+// :321-358).  One warp owns one causal SNP row and streams it with coalesced
+// 16-byte vector loads.  Nothing is unpacked: with lo = even bits, hi = odd
+// bits of the packed row,
+//     n3 (missing, bits 01) = popc(lo) - popc(lo&hi)
+//     n1 (het,     bits 10) = popc(hi) - popc(lo&hi)
+//     n2 (hom A2,  bits 11) = popc(lo&hi)
+//     n0 (hom A1,  bits 00) = N - n1 - n2 - n3
+// so row padding (which decodes as 00) never has to be counted.  POPC issues
+// at 16 lanes/clk/SM, so the raw words go through a Harley-Seal carry-save
+// tree (full-rate LOP3) and only the "fours" word is popcounted: 4 POPC per
+// 64 genotypes instead of 12.  Lane partials are combined with
+// __reduce_add_sync.
+//
+// Algorithmic bytes per SNP: ceil(N/4) read + 16 (counts) + 8 (freq) written.
+#include "ctx.cuh"
+
+namespace {
+
+constexpr uint32_t kLoMask = 0x55555555u;
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+struct LaneCounts {
+    uint32_t ones = 0, twos = 0;      // carry-save state of the raw words
+    uint32_t four_all = 0, four_lo = 0;  // popcounts of the weight-4 words
+    uint32_t both = 0;                // popc(lo & hi)
+
+    __device__ __forceinline__ void add(const uint4 v)
+    {
+        // carry-save adders: (a,b,c) -> sum a^b^c (weight 1), maj(a,b,c) (weight 2)
+        uint32_t t1 = (ones & v.x) | (ones & v.y) | (v.x & v.y);
+        ones = ones ^ v.x ^ v.y;
+        uint32_t t2 = (ones & v.z) | (ones & v.w) | (v.z & v.w);
+        ones = ones ^ v.z ^ v.w;
+        uint32_t f = (twos & t1) | (twos & t2) | (t1 & t2);
+        twos = twos ^ t1 ^ t2;
+        four_all += __popc(f);
+        four_lo += __popc(f & kLoMask);
+        // lo&hi plane of two words packed into one (even bits: x, odd bits: y)
+        uint32_t p1 = (v.x & (v.x >> 1) & kLoMask) | (v.y & (v.y << 1) & ~kLoMask);
+        uint32_t p2 = (v.z & (v.z >> 1) & kLoMask) | (v.w & (v.w << 1) & ~kLoMask);
+        both += __popc(p1) + __popc(p2);
+    }
+};
+
+__device__ __forceinline__ uint32_t word_mask(int64_t valid_bits, int w)
+{
+    int64_t b = valid_bits - 32 * w;
+    if (b <= 0) return 0u;
+    if (b >= 32) return 0xFFFFFFFFu;
+    return (1u << (int)b) - 1u;
+}
+
+__global__ void __launch_bounds__(256)
+counts_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32_t *__restrict__ rows,
+              int64_t mc, int64_t n_samples, int32_t *__restrict__ counts, double *__restrict__ freq)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row_bytes = (n_samples + 3) >> 2;
+    const int64_t nvec = (row_bytes + 15) >> 4;           // 16-byte vectors holding data
+    const int64_t nfull = nvec - 1;                       // all but the last need no mask
+    const int64_t tail_bits = 2 * n_samples - 128 * nfull;  // valid bits in the last vector
+
+    for (int64_t j = warp_id; j < mc; j += warps_total) {
+        const int64_t r = rows ? (int64_t)rows[j] : j;
+        const uint4 *p = reinterpret_cast<const uint4 *>(panel + r * row_stride);
+        LaneCounts c;
+        int64_t i = lane;
+        for (; i + 96 < nfull; i += 128) {
+            uint4 v0 = ldg_stream(p + i), v1 = ldg_stream(p + i + 32);
+            uint4 v2 = ldg_stream(p + i + 64), v3 = ldg_stream(p + i + 96);
+            c.add(v0); c.add(v1); c.add(v2); c.add(v3);
+        }
+        for (; i < nfull; i += 32) c.add(ldg_stream(p + i));
+        if (lane == (int)(nfull & 31)) {                  // masked last vector
+            uint4 v = ldg_stream(p + nfull);
+            v.x &= word_mask(tail_bits, 0); v.y &= word_mask(tail_bits, 1);
+            v.z &= word_mask(tail_bits, 2); v.w &= word_mask(tail_bits, 3);
+            c.add(v);
+        }
+        uint32_t all = 4u * c.four_all + 2u * __popc(c.twos) + __popc(c.ones);
+        uint32_t lo = 4u * c.four_lo + 2u * __popc(c.twos & kLoMask) + __popc(c.ones & kLoMask);
+        all = __reduce_add_sync(0xFFFFFFFFu, all);
+        lo = __reduce_add_sync(0xFFFFFFFFu, lo);
+        uint32_t both = __reduce_add_sync(0xFFFFFFFFu, c.both);
+        if (lane == 0) {
+            const int n2 = (int)both;
+            const int n3 = (int)(lo - both);
+            const int n1 = (int)(all - lo - both);
+            const int n0 = (int)n_samples - n1 - n2 - n3;
+            if (counts) reinterpret_cast<int4 *>(counts)[j] = make_int4(n0, n1, n2, n3);
+            if (freq) {
+                const int nm = n2 + n1 + n0;               // source.cc:874
+                freq[j] = (nm == 0) ? 0.0                  // source.cc:875
+                                    : static_cast<double>(2 * n0 + 1 * n1) / static_cast<double>(2 * nm);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts, double *d_freq)
+{
+    if (mc <= 0) return SIMU_B200_OK;
+    const int warps_per_block = 8;
+    int64_t blocks = (mc + warps_per_block - 1) / warps_per_block;
+    const int64_t max_blocks = (int64_t)ctx->num_sms * 8;   // 64 resident warps per SM
+    if (blocks > max_blocks) blocks = max_blocks;
+    counts_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>(
+        ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_counts, d_freq);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "counts_kernel launch");
+}

@@ -1,0 +1,77 @@
+// Internal declarations shared by the kernels and the C-ABI layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/simu_b200.h"
+
+#define SIMU_B200_VERSION 100
+#define SIMU_ROW_ALIGN 128            // HBM row pitch granularity (bytes)
+#define SIMU_STAGE_BYTES (64u << 20)  // pinned staging chunk (2 of them)
+#define SIMU_NUM_SMS_DEFAULT 148
+
+struct simu_b200_ctx {
+    int device = 0;
+    int num_sms = SIMU_NUM_SMS_DEFAULT;
+    int64_t n_samples = 0;
+    int64_t row_bytes = 0;    // ceil(N/4)
+    int64_t row_stride = 0;   // pitch in HBM
+    uint8_t *panel = nullptr;
+    int64_t panel_rows = 0;
+
+    cudaStream_t own_stream = nullptr;   // created by open
+    cudaStream_t stream = nullptr;       // stream in use (own or external)
+    cudaStream_t copy_stream = nullptr;  // side stream for staging
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint8_t *pinned[2] = {nullptr, nullptr};
+
+    // grow-on-demand device scratch
+    void *scratch[12] = {nullptr};
+    size_t scratch_bytes[12] = {0};
+
+    int64_t launches = 0;
+    float last_ms[2] = {0.f, 0.f};
+    std::string err;
+};
+
+enum ScratchSlot {
+    SCR_ROWS = 0, SCR_COUNTS, SCR_FREQ, SCR_X1, SCR_X2, SCR_Y1, SCR_Y2, SCR_NOISE,
+    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC
+};
+
+int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...);
+int ctx_cuda(simu_b200_ctx *ctx, cudaError_t e, const char *what);
+void *ctx_scratch(simu_b200_ctx *ctx, int slot, size_t bytes);  // nullptr on failure (error set)
+
+#define CUDA_TRY(ctx, expr)                                          \
+    do {                                                             \
+        cudaError_t _e = (expr);                                     \
+        if (_e != cudaSuccess) return ctx_cuda((ctx), _e, #expr);    \
+    } while (0)
+
+// ---- kernel launchers (each returns a simu_b200_status) --------------------
+
+// kernel (a): per-SNP allele counts + frequency.  counts.cu
+int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts, double *d_freq);
+
+// kernel (b), exact FP64 ordered mode.  pheno_exact.cu
+int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                       const double *d_x1, const double *d_x2, double *d_y1, double *d_y2);
+
+// kernel (b), fast FP32 4-SNP LUT mode.  pheno_lut.cu
+int launch_pheno_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                     const double *d_x1, const double *d_x2, double *d_y1, double *d_y2);
+
+// kernel (c): reductions.  reduce.cu
+int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out);
+int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
+                        const double *d_sumsq, double *d_coef);
+int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index);
+
+// synthetic panel generator.  synth.cu
+int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, int64_t n_rows, int64_t dst_row);

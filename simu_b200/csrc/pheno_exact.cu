@@ -1,0 +1,110 @@
+// Kernel (b), EXACT mode: y[i] += ((2 - code_ij) - 2 f_j) * x_jk in FP64, per
+// sample in ascending causal-SNP order with separate subtract / multiply / add
+// -- the arithmetic of /root/reference/src/source.cc:986-996 (an x86-64 build
+// without -march has no FMA contraction), so the result is bit-identical to
+// the reference on one GPU.
+//
+// One thread owns one packed byte column = 4 samples and walks every causal
+// row in order.  The per-SNP products (a - avg) * x for a in {2,1,0} are the
+// same three doubles for every sample, so each block computes them once per
+// 64-SNP chunk into shared memory (index = raw 2-bit field: 00 -> a=2,
+// 01 -> missing -> +0.0, 10 -> a=1, 11 -> a=0) and the inner loop is one
+// shared-memory gather plus one DADD per update.  Adding +0.0 for a missing
+// genotype equals the reference's `continue` because the accumulator can
+// never be -0.0 (it starts at +0.0, and x + (-x) rounds to +0.0).
+//
+// This mode is FP64-pipe / shared-memory bound, not HBM bound; it is the
+// parity anchor.  The FAST mode (pheno_lut.cu) is the throughput path.
+#include "ctx.cuh"
+
+namespace {
+
+constexpr int kChunk = 64;      // SNPs per shared-memory table refill
+constexpr int kThreads = 128;   // byte columns per block (512 samples)
+constexpr int kPrefetch = 8;    // row bytes fetched ahead per thread
+
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32_t *__restrict__ rows,
+                   int64_t mc, int64_t n_samples, const double *__restrict__ freq,
+                   const double *__restrict__ x1, const double *__restrict__ x2,
+                   double *__restrict__ y1, double *__restrict__ y2)
+{
+    __shared__ double tbl[kChunk][4][K];      // [snp][raw bits][trait]
+    __shared__ int64_t row_off[kChunk];
+
+    const int64_t row_bytes = (n_samples + 3) >> 2;
+    const int64_t col = (int64_t)blockIdx.x * kThreads + threadIdx.x;   // byte column
+    const bool active = col < row_bytes;
+    const uint8_t *base = panel + (active ? col : 0);
+
+    double acc[4][K];
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[s][k] = 0.0;
+
+    for (int64_t j0 = 0; j0 < mc; j0 += kChunk) {
+        const int nj = (int)min((int64_t)kChunk, mc - j0);
+        __syncthreads();
+        if (threadIdx.x < nj) {
+            const int64_t j = j0 + threadIdx.x;
+            const double avg = __dmul_rn(2.0, freq[j]);          // source.cc:986
+            row_off[threadIdx.x] = (rows ? (int64_t)rows[j] : j) * row_stride;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const double x = (k == 0) ? x1[j] : x2[j];
+                tbl[threadIdx.x][0][k] = __dmul_rn(__dsub_rn(2.0, avg), x);   // bits 00: two A1 copies
+                tbl[threadIdx.x][1][k] = 0.0;                                 // bits 01: missing (:991)
+                tbl[threadIdx.x][2][k] = __dmul_rn(__dsub_rn(1.0, avg), x);   // bits 10: one copy
+                tbl[threadIdx.x][3][k] = __dmul_rn(__dsub_rn(0.0, avg), x);   // bits 11: none
+            }
+        }
+        __syncthreads();
+        for (int jj = 0; jj < nj; jj += kPrefetch) {
+            uint32_t g[kPrefetch];
+#pragma unroll
+            for (int u = 0; u < kPrefetch; u++)
+                g[u] = (jj + u < nj) ? (uint32_t)__ldg(base + row_off[jj + u]) : 0u;
+#pragma unroll
+            for (int u = 0; u < kPrefetch; u++) {
+                if (jj + u < nj) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        const uint32_t v = (g[u] >> (2 * s)) & 3u;
+#pragma unroll
+                        for (int k = 0; k < K; k++)
+                            acc[s][k] = __dadd_rn(acc[s][k], tbl[jj + u][v][k]);   // source.cc:994-995
+                    }
+                }
+            }
+        }
+    }
+
+    if (active) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int64_t i = 4 * col + s;
+            if (i < n_samples) {
+                y1[i] = acc[s][0];
+                if (K == 2) y2[i] = acc[s][K - 1];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                       const double *d_x1, const double *d_x2, double *d_y1, double *d_y2)
+{
+    const int64_t blocks = (ctx->row_bytes + kThreads - 1) / kThreads;
+    if (d_x2 && d_y2)
+        pheno_exact_kernel<2><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
+            ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
+    else
+        pheno_exact_kernel<1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
+            ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, nullptr, d_y1, nullptr);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "pheno_exact_kernel launch");
+}

@@ -1,0 +1,233 @@
+// Kernel group (c): the scalar reductions that follow find_pheno.
+//
+//   sumsq            sum_i y_i^2                    source.cc:1009-1012
+//   heritability     gen/env coefficients + y = y*gen + noise*env
+//                                                   source.cc:1018-1027
+//   argsort_f64      the sorted order that apply_liability_threshold takes
+//                    with std::sort                 source.cc:1032-1034
+//
+// All three are O(N) / O(N log N) on N <= 500K doubles: latency bound, a few
+// launches each.  They are deterministic (fixed reduction tree, stable LSD
+// radix sort) so repeated runs give identical bits.
+#include <float.h>
+
+#include "ctx.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ sumsq
+
+constexpr int kRedThreads = 256;
+constexpr int kRedItems = 16;   // doubles per thread per block
+
+__device__ __forceinline__ double block_sum(double v, double *smem)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = (lane < (blockDim.x >> 5)) ? smem[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    }
+    return v;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+sumsq_partial_kernel(const double *__restrict__ y, int64_t n, double *__restrict__ partial)
+{
+    __shared__ double smem[32];
+    const int64_t base = (int64_t)blockIdx.x * kRedThreads * kRedItems;
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < kRedItems; u++) {
+        const int64_t i = base + (int64_t)u * kRedThreads + threadIdx.x;
+        if (i < n) { const double v = y[i]; s += v * v; }
+    }
+    s = block_sum(s, smem);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+sum_final_kernel(const double *__restrict__ partial, int64_t np, double *__restrict__ out)
+{
+    __shared__ double smem[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < np; i += kRedThreads) s += partial[i];
+    s = block_sum(s, smem);
+    if (threadIdx.x == 0) *out = s;
+}
+
+// ----------------------------------------------------------- heritability
+
+__global__ void __launch_bounds__(256)
+heritability_kernel(float hsq, double *__restrict__ y, int64_t n, const double *__restrict__ noise,
+                    const double *__restrict__ sumsq, double *__restrict__ coef)
+{
+    double pheno_var = *sumsq / static_cast<double>(n);                       // source.cc:1012
+    double gen_coef, env_coef;
+    if ((fabs((double)hsq) <= (double)FLT_EPSILON) || (fabs(pheno_var) <= (double)FLT_EPSILON)) {
+        gen_coef = 0; env_coef = 1;                                           // :1019-1021
+    } else {
+        gen_coef = sqrt(hsq / pheno_var);                                     // :1023
+        env_coef = sqrt(1.0 - hsq);                                           // :1024
+    }
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && coef) { coef[0] = gen_coef; coef[1] = env_coef; }
+    if (i < n)                                                                // :1027, no FMA contraction
+        y[i] = __dadd_rn(__dmul_rn(y[i], gen_coef), __dmul_rn(noise[i], env_coef));
+}
+
+// ---------------------------------------------------------------- argsort
+
+constexpr int kSortTile = 1024;     // elements per warp
+constexpr int kSortWarps = 4;       // warps per block
+
+__device__ __forceinline__ uint64_t f64_sort_key(double v)
+{
+    uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);   // ascending order as unsigned
+}
+
+__global__ void sort_init_kernel(const double *__restrict__ y, int64_t n, uint64_t *__restrict__ keys,
+                                 int32_t *__restrict__ vals)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = f64_sort_key(y[i]); vals[i] = (int32_t)i; }
+}
+
+// hist[digit * tiles + tile] = number of keys of this tile with this digit
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_hist_kernel(const uint64_t *__restrict__ keys, int64_t n, int shift, int64_t tiles,
+                 uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t cnt[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * kSortWarps + warp;
+    for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
+    __syncwarp();
+    if (tile < tiles) {
+        const int64_t lo = tile * kSortTile, hi = min(n, lo + kSortTile);
+        for (int64_t i = lo + lane; i < hi; i += 32)
+            atomicAdd(&cnt[warp][(keys[i] >> shift) & 0xFF], 1u);
+        __syncwarp();
+        for (int d = lane; d < 256; d += 32) hist[(int64_t)d * tiles + tile] = cnt[warp][d];
+    }
+}
+
+// exclusive scan of hist (length len) in place, one block
+__global__ void __launch_bounds__(1024)
+sort_scan_kernel(uint32_t *__restrict__ hist, int64_t len)
+{
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (len + 1023) / 1024;
+    const int64_t lo = min(len, per * threadIdx.x), hi = min(len, lo + per);
+    uint32_t s = 0;
+    for (int64_t i = lo; i < hi; i++) s += hist[i];
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        warp_sum[lane] = wi - w;   // exclusive
+    }
+    __syncthreads();
+    uint32_t run = warp_sum[warp] + (incl - s);
+    for (int64_t i = lo; i < hi; i++) { uint32_t v = hist[i]; hist[i] = run; run += v; }
+}
+
+// stable scatter: a warp walks its tile 32 keys at a time
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restrict__ vals_in, int64_t n,
+                    int shift, int64_t tiles, const uint32_t *__restrict__ offs,
+                    uint64_t *__restrict__ keys_out, int32_t *__restrict__ vals_out)
+{
+    __shared__ uint32_t pos[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * kSortWarps + warp;
+    if (tile >= tiles) return;
+    for (int d = lane; d < 256; d += 32) pos[warp][d] = offs[(int64_t)d * tiles + tile];
+    __syncwarp();
+    const int64_t lo = tile * kSortTile, hi = min(n, lo + kSortTile);
+    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const bool ok = i < hi;
+        const uint64_t k = ok ? keys_in[i] : 0;
+        const int32_t v = ok ? vals_in[i] : 0;
+        const uint32_t d = ok ? (uint32_t)((k >> shift) & 0xFF) : 256u + lane;   // inactive lanes never match
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t dst = 0;
+        if (ok) dst = pos[warp][d] + rank;
+        __syncwarp();
+        if (ok && rank == 0) pos[warp][d] += __popc(peers);
+        __syncwarp();
+        if (ok) { keys_out[dst] = k; vals_out[dst] = v; }
+    }
+}
+
+}  // namespace
+
+int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out)
+{
+    if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "sumsq: n must be positive");
+    const int64_t per_block = (int64_t)kRedThreads * kRedItems;
+    const int64_t blocks = (n + per_block - 1) / per_block;
+    double *partial = (double *)ctx_scratch(ctx, SCR_MISC, (size_t)blocks * sizeof(double));
+    if (!partial) return SIMU_B200_ENOMEM;
+    sumsq_partial_kernel<<<(unsigned)blocks, kRedThreads, 0, ctx->stream>>>(d_y, n, partial);
+    sum_final_kernel<<<1, kRedThreads, 0, ctx->stream>>>(partial, blocks, d_out);
+    ctx->launches += 2;
+    return ctx_cuda(ctx, cudaGetLastError(), "sumsq launch");
+}
+
+int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
+                        const double *d_sumsq, double *d_coef)
+{
+    if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "heritability: n must be positive");
+    heritability_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(hsq, d_y, n, d_noise, d_sumsq, d_coef);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "heritability launch");
+}
+
+int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index)
+{
+    if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "argsort: n must be positive");
+    const int64_t tiles = (n + kSortTile - 1) / kSortTile;
+    const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
+    const size_t hb = ((size_t)tiles * 256 * 4 + 255) & ~(size_t)255;
+    uint8_t *s = (uint8_t *)ctx_scratch(ctx, SCR_SORT, 2 * kb + 2 * vb + hb);
+    if (!s) return SIMU_B200_ENOMEM;
+    uint64_t *k0 = (uint64_t *)s, *k1 = (uint64_t *)(s + kb);
+    int32_t *v0 = (int32_t *)(s + 2 * kb), *v1 = (int32_t *)(s + 2 * kb + vb);
+    uint32_t *hist = (uint32_t *)(s + 2 * kb + 2 * vb);
+    const unsigned tb = (unsigned)((tiles + kSortWarps - 1) / kSortWarps);
+    sort_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_key, n, k0, v0);
+    ctx->launches++;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 8 * pass;
+        int32_t *vout = (pass == 7) ? d_index : v1;
+        sort_hist_kernel<<<tb, kSortWarps * 32, 0, ctx->stream>>>(k0, n, shift, tiles, hist);
+        sort_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, tiles * 256);
+        sort_scatter_kernel<<<tb, kSortWarps * 32, 0, ctx->stream>>>(k0, v0, n, shift, tiles, hist, k1, vout);
+        ctx->launches += 3;
+        uint64_t *tk = k0; k0 = k1; k1 = tk;
+        int32_t *tv = v0; v0 = v1; v1 = tv;
+    }
+    return ctx_cuda(ctx, cudaGetLastError(), "argsort launch");
+}

@@ -1,0 +1,331 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs.  Bars (north_star):
+
+* allele counts, frequencies, sorted order: bit-exact;
+* find_pheno EXACT mode on one GPU: bit-exact (FP64, ordered);
+* find_pheno FAST mode: |dy| <= 1e-5 * max|y|   (stated tolerance, FP32 LUT + FP64 flush);
+* apply_heritability: <= 1e-12 relative (parallel FP64 sum of squares vs sequential).
+
+Run with `-m gpu` on a B200.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from simu_b200 import capi, plink
+from simu_b200.hotpath import HotPath
+
+pytestmark = pytest.mark.gpu
+
+PANEL_SEED = 20240901
+FAST_RTOL = 1e-5
+
+
+def _effects(mc, seed, k2=True):
+    rng = np.random.default_rng(seed)
+    x1 = rng.standard_normal(mc)
+    x2 = 0.5 * x1 + np.sqrt(1 - 0.25) * rng.standard_normal(mc) if k2 else None
+    return x1, x2
+
+
+def _panel(n, m):
+    return oracle.synth_rows(PANEL_SEED, 0, m, n)
+
+
+# ------------------------------------------------------------------ golden
+
+def test_golden_rows_through_the_abi():
+    """bed_test.c:237-329 vectors: 0x78 -> [0,1,2,3], 0x2d -> [3,2,1,0]."""
+    with capi.Context(4) as ctx:
+        ctx.panel_alloc(2)
+        ctx.panel_put_rows(0, np.array([[0x78], [0x2D]], np.uint8))
+        counts, freq = ctx.find_freq()
+        assert counts.tolist() == [[1, 1, 1, 1], [1, 1, 1, 1]]
+        assert freq.tolist() == [0.5, 0.5]
+        for mode in (capi.MODE_EXACT, capi.MODE_FAST):
+            y1, y2 = ctx.find_pheno(freq, [1.0, 10.0], [2.0, -1.0], mode=mode)
+            assert y1.tolist() == [1.0, -10.0, -1.0, 10.0]
+            assert y2.tolist() == [2.0, 1.0, -2.0, -1.0]
+
+
+def test_synth_generator_matches_host():
+    n, m = 1003, 37
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m)
+        ctx.panel_synth(PANEL_SEED, 5, m)
+        dev = ctx.panel_get_rows(0, m)
+    assert np.array_equal(dev, oracle.synth_rows(PANEL_SEED, 5, m, n))
+
+
+# ------------------------------------------------------------------ counts
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 63, 64, 65, 127, 128, 129, 511, 513, 1000, 4097, 10000, 33333])
+def test_counts_bit_exact_ragged_n(n):
+    m = 41
+    rows = _panel(n, m)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m)
+        ctx.panel_put_rows(0, rows)
+        counts, freq = ctx.find_freq()
+    oc, of = oracle.find_freq(rows, n)
+    assert np.array_equal(counts, oc)
+    assert np.array_equal(freq, of)          # same IEEE expression -> same bits
+
+
+def test_counts_ignore_padding_garbage_and_handle_all_missing():
+    n = 13
+    rows = _panel(n, 6)
+    B = plink.row_bytes(n)
+    rows[:, B - 1] |= 0xFC                  # garbage in the 3 padding pairs of the last byte
+    rows[3, :] = 0x55                       # an all-missing SNP -> freq 0 (source.cc:875)
+    wide = np.full((6, B + 9), 0xFF, np.uint8)   # host stride > row bytes, garbage beyond
+    wide[:, :B] = rows
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(6)
+        ctx.panel_put_rows(0, wide)
+        counts, freq = ctx.find_freq()
+    oc, of = oracle.find_freq(rows, n)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+    assert counts[3].tolist() == [0, 0, 0, n] and freq[3] == 0.0
+
+
+def test_counts_gather_by_row_list():
+    n, m = 2500, 300
+    rows = _panel(n, m)
+    sel = np.sort(np.random.default_rng(1).choice(m, 77, replace=False)).astype(np.int32)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m)
+        ctx.panel_put_rows(0, rows)
+        counts, freq = ctx.find_freq(rows=sel)
+    oc, of = oracle.find_freq(rows, n, row_index=sel)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+
+
+# -------------------------------------------------------------- find_pheno
+
+@pytest.mark.parametrize("n,mc,k2", [(1, 5, False), (7, 1, True), (64, 64, True), (257, 130, False),
+                                     (1000, 333, True), (4099, 257, True), (10000, 1000, False)])
+def test_pheno_exact_bit_identical(n, mc, k2):
+    rows = _panel(n, mc)
+    _, freq = oracle.find_freq(rows, n)
+    x1, x2 = _effects(mc, n + mc, k2)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc)
+        ctx.panel_put_rows(0, rows)
+        y1, y2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_EXACT)
+    o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2)
+    assert np.array_equal(y1, o1)
+    if k2:
+        assert np.array_equal(y2, o2)
+
+
+@pytest.mark.parametrize("n,mc,k2", [(1, 5, False), (7, 1, True), (64, 64, True), (257, 130, False),
+                                     (1000, 333, True), (4099, 257, True), (10000, 1000, False),
+                                     (9001, 4100, True), (20000, 3000, False)])
+def test_pheno_fast_within_tolerance(n, mc, k2):
+    rows = _panel(n, mc)
+    _, freq = oracle.find_freq(rows, n)
+    x1, x2 = _effects(mc, 3 * n + mc, k2)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc)
+        ctx.panel_put_rows(0, rows)
+        y1, y2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+    o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2)
+    assert np.max(np.abs(y1 - o1)) <= FAST_RTOL * max(np.max(np.abs(o1)), 1e-300)
+    if k2:
+        assert np.max(np.abs(y2 - o2)) <= FAST_RTOL * max(np.max(np.abs(o2)), 1e-300)
+
+
+@pytest.mark.parametrize("mode", [capi.MODE_EXACT, capi.MODE_FAST])
+def test_pheno_gather_missing_and_scaled_effects(mode):
+    """--gcta-sigma style effects (x / sqrt(2p(1-p))), a row list, heavy missingness."""
+    n, m = 3001, 400
+    rows = _panel(n, m)
+    rng = np.random.default_rng(5)
+    miss = rng.random((m, n)) < 0.2
+    codes = np.stack([oracle.unpack(rows[j], n) for j in range(m)])
+    codes[miss] = 3
+    rows = np.stack([oracle.pack(codes[j]) for j in range(m)])
+    sel = np.sort(rng.choice(m, 150, replace=False)).astype(np.int32)
+    _, freq = oracle.find_freq(rows, n, row_index=sel)
+    het = np.abs(2 * freq * (1 - freq))
+    x1 = rng.standard_normal(sel.size) * np.sqrt(het ** -1.0)      # source.cc:1257-1258
+    x2 = rng.standard_normal(sel.size) * np.sqrt(het ** -1.0)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m)
+        ctx.panel_put_rows(0, rows)
+        y1, y2 = ctx.find_pheno(freq, x1, x2, rows=sel, mode=mode)
+    o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2, row_index=sel)
+    if mode == capi.MODE_EXACT:
+        assert np.array_equal(y1, o1) and np.array_equal(y2, o2)
+    else:
+        assert np.max(np.abs(y1 - o1)) <= FAST_RTOL * np.max(np.abs(o1))
+        assert np.max(np.abs(y2 - o2)) <= FAST_RTOL * np.max(np.abs(o2))
+
+
+def test_pheno_empty_causal_set():
+    with capi.Context(10) as ctx:
+        ctx.panel_alloc(1)
+        y1, y2 = ctx.find_pheno(np.zeros(0), np.zeros(0), np.zeros(0))
+        assert not y1.any() and not y2.any()
+        counts, freq = ctx.find_freq(mc=0)
+        assert counts.shape == (0, 4) and freq.size == 0
+
+
+@pytest.mark.parametrize("mode", [capi.MODE_EXACT, capi.MODE_FAST])
+def test_pheno_linearity_property_config1_shape(mode):
+    """Size-independent property at config-1 shape (10K x 1000 causal):
+    y(x_a + x_b) == y(x_a) + y(x_b) and y(c x) == c y(x) up to rounding."""
+    n, mc = 10000, 1000
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc)
+        ctx.panel_synth(PANEL_SEED, 0, mc)
+        _, freq = ctx.find_freq()
+        xa, xb = _effects(mc, 11, True)
+        ya, _ = ctx.find_pheno(freq, xa, mode=mode)
+        yb, _ = ctx.find_pheno(freq, xb, mode=mode)
+        ys, y3 = ctx.find_pheno(freq, xa + xb, 3.0 * xa, mode=mode)
+    scale = np.max(np.abs(ys))
+    assert np.max(np.abs(ys - (ya + yb))) <= 2e-5 * scale
+    assert np.max(np.abs(y3 - 3.0 * ya)) <= 2e-5 * np.max(np.abs(y3))
+    # centred genotypes: sum_i y_i == -sum_j 2 f_j x_j m_j ... for SNPs without missing data the
+    # column of centred dosages sums to zero, so |mean(y)| stays tiny next to |y|
+    assert abs(ya.mean()) < 0.05 * np.abs(ya).max()
+
+
+# ---------------------------------------------------------------- kernel (c)
+
+def test_apply_heritability_parity():
+    rng = np.random.default_rng(3)
+    n = 12345
+    y = rng.standard_normal(n) * 7.0
+    noise = rng.standard_normal(n)
+    eff = rng.standard_normal(50)
+    with capi.Context(n) as ctx:
+        for hsq in (0.5, 0.7, 0.0, 1.0):
+            gy, ge, gen, env = ctx.apply_heritability(hsq, y, noise, eff)
+            oy, oe, ogen, oenv = oracle.apply_heritability(float(np.float32(hsq)), y, noise, eff)
+            assert env == oenv
+            assert abs(gen - ogen) <= 1e-12 * max(abs(ogen), 1.0)
+            assert np.max(np.abs(gy - oy)) <= 1e-12 * np.max(np.abs(oy))
+            assert np.max(np.abs(ge - oe)) <= 1e-12 * max(np.max(np.abs(oe)), 1.0)
+        # all-zero phenotype: pheno_var <= FLT_EPSILON -> gen 0, env 1 (source.cc:1019-1021)
+        gy, _, gen, env = ctx.apply_heritability(0.5, np.zeros(n), noise, None)
+        assert (gen, env) == (0.0, 1.0) and np.array_equal(gy, noise)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 1000, 1024, 1025, 100000])
+def test_liability_order_bit_exact(n):
+    rng = np.random.default_rng(n)
+    y = rng.standard_normal(n)
+    if n > 10:
+        y[rng.integers(0, n, n // 5)] = 0.25          # ties
+        y[rng.integers(0, n, 3)] = -0.0
+        y[0], y[1] = np.inf, -np.inf
+    with capi.Context(max(n, 4)) as ctx:
+        idx = ctx.liability_order(y)
+    assert sorted(idx.tolist()) == list(range(n))
+    assert np.array_equal(y[idx], np.sort(y))
+    # ties resolved by sample index (stable), like the oracle's comparator -- except that
+    # -0.0 sorts before +0.0 here; the reference's std::sort leaves all ties unspecified
+    if not np.any((y == 0) & np.signbit(y)):
+        assert np.array_equal(idx, oracle.liability_order(y))
+
+
+def test_liability_threshold_labels_agree_with_oracle():
+    n = 5000
+    rng = np.random.default_rng(9)
+    y = rng.standard_normal(n)
+    k = 0.1
+    perm_rng = np.random.default_rng(1)
+
+    def shuffle(lst):
+        a = np.array(lst)
+        perm_rng.shuffle(a)
+        return a.tolist()
+
+    with capi.Context(n) as ctx:
+        hp = HotPath(ctx)
+        lab = hp.apply_liability_threshold(k, 300, 700, shuffle, y)
+    perm_rng = np.random.default_rng(1)
+    max_cas, max_con = oracle.liability_split(k, n)
+    con = np.arange(max_con); perm_rng.shuffle(con)
+    cas = np.arange(max_con, n); perm_rng.shuffle(cas)
+    olab = oracle.liability_labels(k, 300, 700, oracle.liability_order(y), con, cas)
+    assert np.array_equal(lab, olab)
+    assert (np.count_nonzero(lab == 2), np.count_nonzero(lab == 1)) == (300, 700)
+
+
+# ------------------------------------------------------- staging from .bed
+
+def test_load_bed_causal_rows_only(tmp_path):
+    n, m = 777, 120
+    rows = _panel(n, m)
+    prefix = str(tmp_path / "syn")
+    plink.write_fileset(prefix, rows, n)
+    sel = np.sort(np.random.default_rng(2).choice(m, 40, replace=False))
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(40)
+        ctx.panel_load_bed(prefix + ".bed", m, sel)
+        assert np.array_equal(ctx.panel_get_rows(0, 40), rows[sel])
+        counts, _ = ctx.find_freq()
+    assert np.array_equal(counts, oracle.find_freq(rows, n, row_index=sel)[0])
+
+
+def test_load_bed_errors(tmp_path):
+    n, m = 50, 10
+    rows = _panel(n, m)
+    prefix = str(tmp_path / "syn")
+    plink.write_fileset(prefix, rows, n)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m)
+        # sample-major header -> "snps must be rows" (source.cc:196-200)
+        bad = str(tmp_path / "bad.bed")
+        open(bad, "wb").write(bytes([0x6C, 0x1B, 0x00]) + rows[:, :plink.row_bytes(n)].tobytes())
+        with pytest.raises(capi.SimuB200Error) as ei:
+            ctx.panel_load_bed(bad, m)
+        assert ei.value.status == capi.EFORMAT and "snps must be rows" in str(ei.value)
+        # truncated file -> read error (bed.c:349-352 -> source.cc:226-229)
+        short = str(tmp_path / "short.bed")
+        open(short, "wb").write(open(prefix + ".bed", "rb").read()[:-7])
+        with pytest.raises(capi.SimuB200Error) as ei:
+            ctx.panel_load_bed(short, m)
+        assert ei.value.status == capi.ERROR and "Error reading from" in str(ei.value)
+        # .bim announces fewer loci than requested row -> END (source.cc:855-858)
+        with pytest.raises(capi.SimuB200Error) as ei:
+            ctx.panel_load_bed(prefix + ".bed", m, np.array([3, m]))
+        assert ei.value.status == capi.END and "expect to find" in str(ei.value)
+        with pytest.raises(capi.SimuB200Error):
+            ctx.panel_load_bed(str(tmp_path / "nope.bed"), m)
+
+
+def test_hotpath_mirror_bfile_chr(tmp_path):
+    """--bfile-chr: 3 'chromosomes' concatenated in label order (source.cc:434-443, :277-307);
+    the mirror's find_freq / find_pheno against the oracle over the concatenated rows."""
+    n = 501
+    sizes = [30, 17, 45]
+    rows = _panel(n, sum(sizes))
+    off = 0
+    for lab, sz in zip(("1", "2", "3"), sizes):
+        plink.write_fileset(str(tmp_path / f"chr{lab}"), rows[off:off + sz], n, chromosome=int(lab), first_index=off)
+        off += sz
+    pf = plink.PlinkFiles.from_bfile_chr(str(tmp_path / "chr@"), labels=["1", "2", "3"])
+    assert (pf.num_variants, pf.num_samples) == (sum(sizes), n)
+    assert pf.get_locus(31).name == "rs31" and pf.get_locus(31).chromosome == 2
+    rng = np.random.default_rng(4)
+    comp = np.where(rng.random(pf.num_variants) < 0.5, 0, -1)
+    causal = np.flatnonzero(comp != -1)
+    opts = {"num_variants": pf.num_variants, "num_samples": n, "num_traits": 2}
+    x1 = np.zeros(pf.num_variants); x2 = np.zeros(pf.num_variants)
+    x1[causal], x2[causal] = _effects(causal.size, 8)
+    with capi.Context(n) as ctx:
+        hp = HotPath(ctx, pf)
+        freq_vec, counts = hp.find_freq(opts, comp, return_counts=True)
+        y1, y2 = hp.find_pheno(opts, comp, freq_vec, x1, x2)
+        with pytest.raises(RuntimeError, match="expect to find"):
+            hp.find_freq(opts, comp[:-1])
+    oc, of = oracle.find_freq(rows, n, row_index=causal)
+    assert np.array_equal(counts[causal], oc) and np.array_equal(freq_vec[causal], of)
+    assert np.all(np.isnan(freq_vec[comp == -1]))                       # source.cc:850
+    o1, o2 = oracle.find_pheno(rows, n, of, x1[causal], x2[causal], row_index=causal)
+    assert np.array_equal(y1, o1) and np.array_equal(y2, o2)
