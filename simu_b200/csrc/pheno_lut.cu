@@ -1,8 +1,392 @@
-// placeholder until the LUT kernel lands (next commit): FAST mode reports an error, it never
-// silently falls back to another path.
+// Kernel (b), FAST mode: y[:,k] += sum_j t_jk[g_ij] with 4-SNP lookup tables.
+//
+// Why tables: at the measured 6.4 TB/s a B200 SM has to retire ~90-130
+// genotypes per clock, i.e. about one issue slot per genotype; "shift, mask,
+// select, add" per genotype per trait is 3-5x over that budget.  The
+// contribution of SNP j to a sample is a 4-valued function of the raw 2-bit
+// field v (00 -> x(2-2p), 01 missing -> 0, 10 -> x(1-2p), 11 -> x(-2p)), so
+// four SNP rows are combined into one byte index e and one table of 256
+// entries: one shared-memory load + one add per FOUR genotypes per trait.
+//
+// Layout of one step (64 causal rows x 4096 samples) in a CTA:
+//   * tile: 64 rows x 1024 B in shared memory, filled by one TMA bulk copy
+//     (cp.async.bulk) per row issued by a producer warp;
+//   * table: 16 groups (4 rows each) x 256 entries, 32 KB, precomputed once
+//     per run by lut_build_kernel in FP64 -> FP32, fetched with one bulk copy;
+//   * 8 consumer warps, 512 samples each; a lane owns one 32-bit column word
+//     (16 samples) and keeps its 16*K partial sums in registers.
+// Bank conflicts are designed out: lane l reads word l of every row (bank l),
+// and at sub-step t it works on group (l+t) mod 16, whose table column sits in
+// bank (l+t) mod 16 (+16 for the upper half-warp, which uses a replica of the
+// table; for K=2 the 8-byte entries make each half-warp its own wavefront).
+// The 4 row words are bit-transposed to 16 byte indices with 16 LOP3/SHF.
+//
+// Work is split over min(#SM, steps) persistent CTAs as contiguous ranges of the
+// (sample-tile major, row-block minor) step list, so the load is balanced to
+// within one step; a CTA flushes its FP32 partial sums to a private FP64
+// slot every 64 blocks (1024 terms per accumulator, relative rounding error
+// ~1e-6) and at tile boundaries; lut_reduce_kernel adds the slots in a fixed
+// order, so the result is deterministic.
+//
+// Algorithmic bytes: Mc*(ceil(N/4) + 12 + 8K) + 8NK.
 #include "ctx.cuh"
-int launch_pheno_lut(simu_b200_ctx *ctx, const int32_t *, int64_t, const double *, const double *,
-                     const double *, double *, double *)
+
+namespace {
+
+constexpr int kBlockRows = 64;                       // causal rows per step
+constexpr int kGroups = kBlockRows / 4;              // 16 four-row groups
+constexpr int kWarps = 8;                            // consumer warps
+constexpr int kTileSamples = kWarps * 512;           // 4096
+constexpr int kTileBytes = kTileSamples / 4;         // 1024 per row
+constexpr int kTableBytes = 256 * 128;               // 32 KB
+constexpr int kStageBytes = kBlockRows * kTileBytes + kTableBytes;   // 96 KB
+constexpr int kStages = 2;
+constexpr int kFlushBlocks = 64;
+constexpr int kThreads = (kWarps + 1) * 32;
+constexpr int kSmemBytes = kStages * kStageBytes + 64;
+
+// ------------------------------------------------------------- PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
-    return ctx_fail(ctx, SIMU_B200_ERROR, "find_pheno: FAST mode kernel not built yet");
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// Bounded wait: a protocol bug must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (mbar_test(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_test(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// (a & m) | (b & ~m) in one LOP3
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
+// ---------------------------------------------------------------- LUT build
+
+// lut[block][e][128 B]:  K=1: 32 floats, slot = replica*16 + group
+//                        K=2: 16 float2, slot = group -> (trait1, trait2)
+template <int K>
+__global__ void __launch_bounds__(256)
+lut_build_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
+                 int64_t mc, float *__restrict__ lut)
+{
+    __shared__ double T[kBlockRows][4][K];
+    const int64_t b = blockIdx.x;
+    if (threadIdx.x < kBlockRows) {
+        const int64_t j = b * kBlockRows + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double t0 = 0.0, t2 = 0.0, t3 = 0.0;
+            if (j < mc) {
+                const double avg = 2.0 * freq[j];
+                const double x = (k == 0) ? x1[j] : x2[j];
+                t0 = (2.0 - avg) * x;      // bits 00: two A1 copies
+                t2 = (1.0 - avg) * x;      // bits 10: one copy
+                t3 = (0.0 - avg) * x;      // bits 11: none
+            }
+            T[threadIdx.x][0][k] = t0;
+            T[threadIdx.x][1][k] = 0.0;    // bits 01: missing contributes 0 (source.cc:991)
+            T[threadIdx.x][2][k] = t2;
+            T[threadIdx.x][3][k] = t3;
+        }
+    }
+    __syncthreads();
+    const int e = threadIdx.x;
+    float out[32];
+#pragma unroll
+    for (int g = 0; g < kGroups; g++) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double s = T[4 * g + 0][e & 3][k] + T[4 * g + 1][(e >> 2) & 3][k];
+            s += T[4 * g + 2][(e >> 4) & 3][k] + T[4 * g + 3][(e >> 6) & 3][k];
+            if (K == 1) { out[g] = (float)s; out[16 + g] = (float)s; }
+            else out[2 * g + k] = (float)s;
+        }
+    }
+    float4 *dst = reinterpret_cast<float4 *>(lut + (b * 256 + e) * 32);
+#pragma unroll
+    for (int q = 0; q < 8; q++) dst[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+}
+
+// ---------------------------------------------------------------- main kernel
+
+struct LutParams {
+    const uint8_t *panel;
+    int64_t row_stride;
+    const int32_t *rows;
+    int64_t mc;
+    int64_t n_samples;
+    const float *lut;
+    double *ypart;          // [slots][K][npad]
+    int64_t npad;           // tiles * kTileSamples
+    int64_t tiles;
+    int64_t nblocks;
+    int64_t steps;          // tiles * nblocks
+};
+
+__device__ __forceinline__ int64_t cta_of_step(int64_t s, int64_t grid, int64_t steps)
+{
+    return ((s + 1) * grid - 1) / steps;   // largest c with (c*steps)/grid <= s
+}
+
+template <int K>
+__device__ __forceinline__ void lookup4(float (&acc)[16][K], const uint32_t z, const uint32_t tbl, const int s0)
+{
+    // bytes 0..3 of z are the table indices of samples s0, s0+4, s0+8, s0+12
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const uint32_t e = __byte_perm(z, 0, 0x4440 + m);
+        const uint32_t addr = tbl + e * 128u;
+        if (K == 1) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+            acc[s0 + 4 * m][0] += v;
+        } else {
+            float v0, v1;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v0), "=f"(v1) : "r"(addr));
+            acc[s0 + 4 * m][0] += v0;
+            acc[s0 + 4 * m][K - 1] += v1;
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void flush_acc(float (&acc)[16][K], double *__restrict__ ypart, int64_t npad,
+                                          int64_t slot, int64_t sample0)
+{
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double *dst = ypart + (slot * K + k) * npad + sample0;
+#pragma unroll
+        for (int s = 0; s < 16; s += 2) {
+            double2 v = *reinterpret_cast<double2 *>(dst + s);
+            v.x += (double)acc[s][k];
+            v.y += (double)acc[s + 1][k];
+            *reinterpret_cast<double2 *>(dst + s) = v;
+            acc[s][k] = 0.f;
+            acc[s + 1][k] = 0.f;
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1)
+pheno_lut_kernel(const LutParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t grid = gridDim.x, cta = blockIdx.x;
+    const int64_t s_begin = (cta * p.steps) / grid, s_end = ((cta + 1) * p.steps) / grid;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    // full[s] at bar_base + 8*s, empty[s] at bar_base + 16 + 8*s
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(bar_base + 8 * s, 1);
+            mbar_init(bar_base + 16 + 8 * s, kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kWarps) {
+        // ===================== producer warp: TMA bulk copies =====================
+        int64_t it = 0;
+        for (int64_t s = s_begin; s < s_end; s++, it++) {
+            const int stage = (int)(it & 1);
+            const uint32_t parity = (uint32_t)((it >> 1) & 1);
+            const int64_t tile = s / p.nblocks, blk = s - tile * p.nblocks;
+            const uint32_t full = bar_base + 8 * stage, empty = bar_base + 16 + 8 * stage;
+            const uint32_t stage_base = smem_base + stage * kStageBytes;
+            const int64_t col0 = tile * kTileBytes;
+            const uint32_t bytes = (uint32_t)min((int64_t)kTileBytes, p.row_stride - col0);
+            const int64_t j0 = blk * kBlockRows;
+            const int nvalid = (int)min((int64_t)kBlockRows, p.mc - j0);
+            mbar_wait(empty, parity ^ 1u);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(full, (uint32_t)nvalid * bytes + (uint32_t)kTableBytes);
+                bulk_g2s(stage_base + kBlockRows * kTileBytes, p.lut + blk * (kTableBytes / 4), kTableBytes, full);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = lane; r < kBlockRows; r += 32) {
+                if (r < nvalid) {
+                    const int64_t row = p.rows ? (int64_t)p.rows[j0 + r] : (j0 + r);
+                    bulk_g2s(stage_base + r * kTileBytes, p.panel + row * p.row_stride + col0, bytes, full);
+                }
+            }
+        }
+        return;
+    }
+
+    // ========================= consumer warps: lookups =========================
+    float acc[16][K];
+#pragma unroll
+    for (int s = 0; s < 16; s++)
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[s][k] = 0.f;
+
+    int64_t it = 0;
+    int64_t cur_tile = -1, slot = 0;
+    int since_flush = 0;
+    for (int64_t s = s_begin; s < s_end; s++, it++) {
+        const int stage = (int)(it & 1);
+        const uint32_t parity = (uint32_t)((it >> 1) & 1);
+        const int64_t tile = s / p.nblocks;
+        if (tile != cur_tile || since_flush == kFlushBlocks) {
+            if (cur_tile >= 0)
+                flush_acc<K>(acc, p.ypart, p.npad, slot, cur_tile * kTileSamples + warp * 512 + lane * 16);
+            if (tile != cur_tile) {
+                cur_tile = tile;
+                slot = cta - cta_of_step(tile * p.nblocks, grid, p.steps);
+            }
+            since_flush = 0;
+        }
+        since_flush++;
+
+        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 16 + 8 * stage;
+        const uint32_t stage_base = smem_base + stage * kStageBytes;
+        const uint32_t words = stage_base + warp * 128 + lane * 4;        // this lane's column word, row 0
+        const uint32_t table = stage_base + kBlockRows * kTileBytes;
+        mbar_wait(full, parity);
+
+#pragma unroll 2
+        for (int t = 0; t < kGroups; t++) {
+            const uint32_t gi = (uint32_t)(lane + t) & 15u;
+            const uint32_t wa = words + gi * (4u * kTileBytes);
+            uint32_t A, B, C, D;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(A) : "r"(wa));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(B) : "r"(wa + kTileBytes));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(C) : "r"(wa + 2 * kTileBytes));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(D) : "r"(wa + 3 * kTileBytes));
+            // 4 rows x 16 fields  ->  16 bytes (A | B<<2 | C<<4 | D<<6 per sample)
+            const uint32_t X0 = bitsel(A, B << 2, 0x33333333u);     // even samples: nibble = A | B<<2
+            const uint32_t X1 = bitsel(A >> 2, B, 0x33333333u);     // odd samples
+            const uint32_t Y0 = bitsel(C, D << 2, 0x33333333u);
+            const uint32_t Y1 = bitsel(C >> 2, D, 0x33333333u);
+            const uint32_t Z00 = bitsel(X0, Y0 << 4, 0x0F0F0F0Fu);  // samples 0,4,8,12
+            const uint32_t Z01 = bitsel(X0 >> 4, Y0, 0x0F0F0F0Fu);  // samples 2,6,10,14
+            const uint32_t Z10 = bitsel(X1, Y1 << 4, 0x0F0F0F0Fu);  // samples 1,5,9,13
+            const uint32_t Z11 = bitsel(X1 >> 4, Y1, 0x0F0F0F0Fu);  // samples 3,7,11,15
+            const uint32_t tbl = table + (K == 1 ? (gi + (lane & 16u)) * 4u : gi * 8u);
+            lookup4<K>(acc, Z00, tbl, 0);
+            lookup4<K>(acc, Z10, tbl, 1);
+            lookup4<K>(acc, Z01, tbl, 2);
+            lookup4<K>(acc, Z11, tbl, 3);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty);
+    }
+    if (cur_tile >= 0)
+        flush_acc<K>(acc, p.ypart, p.npad, slot, cur_tile * kTileSamples + warp * 512 + lane * 16);
+}
+
+// y[k][i] = sum over the slots of the tile that holds sample i, in slot order
+template <int K>
+__global__ void __launch_bounds__(256)
+lut_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int slots,
+                  double *__restrict__ y1, double *__restrict__ y2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double s = 0.0;
+        for (int q = 0; q < slots; q++) s += ypart[((int64_t)q * K + k) * npad + i];
+        if (k == 0) y1[i] = s; else y2[i] = s;
+    }
+}
+
+template <int K>
+int run_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq, const double *d_x1,
+            const double *d_x2, double *d_y1, double *d_y2)
+{
+    const int64_t n = ctx->n_samples;
+    const int64_t tiles = (n + kTileSamples - 1) / kTileSamples;
+    const int64_t nblocks = (mc + kBlockRows - 1) / kBlockRows;
+    const int64_t steps = tiles * nblocks;
+    const int64_t grid = steps < ctx->num_sms ? steps : ctx->num_sms;
+    const int slots = (int)((grid + tiles - 1) / tiles) + 1;
+    const int64_t npad = tiles * kTileSamples;
+
+    float *lut = (float *)ctx_scratch(ctx, SCR_LUT, (size_t)nblocks * kTableBytes);
+    const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
+    double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
+    if (!lut || !ypart) return SIMU_B200_ENOMEM;
+
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[K]) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set[K] = true;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
+    lut_build_kernel<K><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, lut);
+
+    LutParams p;
+    p.panel = ctx->panel; p.row_stride = ctx->row_stride; p.rows = d_rows; p.mc = mc; p.n_samples = n;
+    p.lut = lut; p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
+    pheno_lut_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p);
+    lut_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, d_y1, d_y2);
+    ctx->launches += 3;
+    return ctx_cuda(ctx, cudaGetLastError(), "pheno_lut launch");
+}
+
+}  // namespace
+
+int launch_pheno_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                     const double *d_x1, const double *d_x2, double *d_y1, double *d_y2)
+{
+    if (mc <= 0) {   // source.cc:962-966: phenotypes start at zero
+        CUDA_TRY(ctx, cudaMemsetAsync(d_y1, 0, (size_t)ctx->n_samples * sizeof(double), ctx->stream));
+        if (d_y2) CUDA_TRY(ctx, cudaMemsetAsync(d_y2, 0, (size_t)ctx->n_samples * sizeof(double), ctx->stream));
+        return SIMU_B200_OK;
+    }
+    if (d_x2 && d_y2) return run_lut<2>(ctx, d_rows, mc, d_freq, d_x1, d_x2, d_y1, d_y2);
+    return run_lut<1>(ctx, d_rows, mc, d_freq, d_x1, nullptr, d_y1, nullptr);
 }
