@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- phenotype-synthesis hot path (y = Gx + e over packed PLINK .bed).
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+    find_freq (allele counts) -> find_pheno (FAST LUT kernel) ->
+    [N>1: one NCCL all-reduce of the partial N x K phenotypes] ->
+    apply_heritability (sum of squares + scale-and-add-noise) per trait
+    [-> liability sort for --cc workloads].
+
+Metric (BASELINE.json): genotype x effect updates per second = N * Mc * K per
+step, whole job over all GPUs; packed-.bed GB/s and the HBM roofline fraction of
+the dominant kernel ride along.  Default workload = BASELINE configs[1]:
+100K individuals x 1M SNPs resident in HBM (25 GB), 100K causal SNPs, 2 traits,
+--gcta-sigma effects.  Data is synthetic (SURVEY.md 8d generator, panel seed
+20240901) and generated on the device.
+
+`--impl reference` times the reference's CPU algorithm (the oracle port of
+src/source.cc:843-1029, single-threaded like the reference) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PANEL_SEED = 20240901
+
+WORKLOADS = {
+    # name: N, M rows resident per GPU, Mc causal per GPU, K traits, cc, description
+    "config1": dict(n=10_000, m=100_000, mc=1_000, k=1, cc=False,
+                    desc="--qt 10K x 100K, --causal-n 1000 --hsq 0.5 --seed 1"),
+    "config2": dict(n=100_000, m=1_000_000, mc=100_000, k=2, cc=False,
+                    desc="--qt --num-traits 2 --rg 0.5 --gcta-sigma --norm-effect, 100K x 1M, --causal-n 100000"),
+    "config3": dict(n=100_000, m=1_000_000, mc=10_000, k=1, cc=True,
+                    desc="--cc --k 0.1, 100K x 1M, --causal-n 10000"),
+    "config4": dict(n=100_000, m=1_375_000, mc=1_375_000, k=1, cc=False,
+                    desc="--bfile-chr @, 100K x 11M fully polygenic, 1/8 of the SNPs per GPU (34.5 GB)"),
+    "config5": dict(n=500_000, m=1_000_000, mc=100_000, k=2, cc=False,
+                    desc="--causal-variants, 2 traits, 500K x 1M (125 GB), 100K causal"),
+}
+HSQ = (0.5, 0.7)
+RG = 0.5
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def _causal_rows(w, rank):
+    rng = np.random.default_rng(1 + rank)            # --seed 1 (+rank: each GPU owns its own slice)
+    if w["mc"] == w["m"]:
+        return np.arange(w["m"], dtype=np.int32)
+    return np.sort(rng.choice(w["m"], w["mc"], replace=False)).astype(np.int32)
+
+
+def _effects(w, freq, rank):
+    """Bivariate normal effects (source.cc:940-948) with --gcta-sigma scaling (:1257-1262)."""
+    rng = np.random.default_rng(1000 + rank)
+    z1, z2 = rng.standard_normal(w["mc"]), rng.standard_normal(w["mc"])
+    het = np.abs(2.0 * freq * (1.0 - freq))
+    scale = np.sqrt(np.power(np.maximum(het, 1e-12), -1.0))
+    x1 = z1 * scale
+    x2 = (RG * z1 + np.sqrt(1.0 - RG * RG) * z2) * scale
+    return x1, (x2 if w["k"] == 2 else None)
+
+
+def alg_bytes(w):
+    B = (w["n"] + 3) // 4
+    counts = w["mc"] * (B + 16 + 8)
+    pheno = w["mc"] * (B + 12 + 8 * w["k"]) + 8 * w["n"] * w["k"]
+    return B, counts, pheno
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.samples, self.proc, self.t = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = [s for s in self.samples if t0 <= s[0] <= t1 + 0.15] or self.samples[-5:]
+        sm, mx, reasons = [], [], set()
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------ reference arm
+
+def cpu_port_time(rows_host, n, k, freq_unused=None, hsq=HSQ):
+    """One pass of the reference algorithm (oracle port) over `rows_host`; -> seconds."""
+    from oracle import oracle
+    mc = rows_host.shape[0]
+    rng = np.random.default_rng(7)
+    t0 = time.perf_counter()
+    _, freq = oracle.find_freq(rows_host, n)
+    x1 = rng.standard_normal(mc)
+    x2 = rng.standard_normal(mc) if k == 2 else None
+    y1, y2 = oracle.find_pheno(rows_host, n, freq, x1, x2)
+    noise = rng.standard_normal(n)
+    oracle.apply_heritability(hsq[0], y1, noise, x1)
+    if k == 2:
+        oracle.apply_heritability(hsq[1], y2, noise, x2)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, w):
+    """The reference's CPU implementation of the path, single-threaded as upstream
+    (/root/reference has no threads: SURVEY.md 0.2).  Source.cc itself needs Boost,
+    which this image lacks, so the line-by-line oracle port is what runs (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    n, k = w["n"], w["k"]
+    causal = _causal_rows(w, 0)
+    probe_rows = 64
+    rows = np.concatenate([oracle.synth_rows(PANEL_SEED, int(r), 1, n) for r in causal[:probe_rows]])
+    t_probe = cpu_port_time(rows, n, k)
+    budget = 150.0
+    per_row = max(t_probe / probe_rows, 1e-7)
+    s = int(max(probe_rows, min(w["mc"], budget / ((args.steps + args.warmup) * per_row))))
+    # synthesize the sample: the first s causal rows of the same panel the GPU arm uses
+    rows = np.empty((s, rows.shape[1]), np.uint8)
+    runs = np.split(np.arange(s), np.flatnonzero(np.diff(causal[:s]) != 1) + 1) if s > 1 else [np.arange(s)]
+    for run in runs:
+        rows[run[0]:run[-1] + 1] = oracle.synth_rows(PANEL_SEED, int(causal[run[0]]), run.size, n)
+    for _ in range(args.warmup):
+        cpu_port_time(rows, n, k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_time(rows, n, k)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n * s * k / dt
+    sample = f"first {s} of {w['mc']} causal SNP rows x {n} samples per step (same panel, same row list)"
+    line = {
+        "impl": "reference", "metric": "genotype_effect_updates_per_s", "value": value, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "n_samples": n, "n_causal": w["mc"],
+                   "traits": k, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "bed_gbs": s * ((n + 3) // 4) * 2 / dt / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+
+class _DevMem:
+    """Zero-copy torch view of library-owned device memory (plumbing only)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from simu_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; simu_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n, m, mc, k = w["n"], w["m"], w["mc"], w["k"]
+    B, bytes_counts, bytes_pheno = alg_bytes(w)
+
+    ctx = capi.Context(n, device=local)
+    stream = torch.cuda.Stream(device=dev)           # one stream for torch ops, NCCL hand-off and our kernels
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.panel_alloc(m)
+    ctx.panel_synth(PANEL_SEED, rank * m, m)        # each GPU holds its own slice of the panel
+    causal = _causal_rows(w, rank)
+    d_rows = torch.from_numpy(causal).to(dev) if mc != m else None
+    rows_ptr = d_rows.data_ptr() if d_rows is not None else 0
+    d_counts = torch.empty((mc, 4), dtype=torch.int32, device=dev)
+    d_freq = torch.empty(mc, dtype=torch.float64, device=dev)
+    ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
+    torch.cuda.synchronize()
+    x1, x2 = _effects(w, d_freq.cpu().numpy(), rank)
+    d_x1 = torch.from_numpy(x1).to(dev)
+    d_x2 = torch.from_numpy(x2).to(dev) if k == 2 else None
+    d_y = torch.zeros((k, n), dtype=torch.float64, device=dev)       # [trait][sample], contiguous for one all-reduce
+    g = torch.Generator(device="cpu").manual_seed(5)
+    d_noise = torch.randn((k, n), dtype=torch.float64, generator=g).to(dev)   # e: same draws on every rank
+    d_misc = torch.zeros(8, dtype=torch.float64, device=dev)
+    d_index = torch.empty(n, dtype=torch.int32, device=dev)
+    mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
+
+    def step():
+        ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
+        ctx.find_pheno_dev(rows_ptr, mc, d_freq.data_ptr(), d_x1.data_ptr(), d_x2.data_ptr() if k == 2 else 0,
+                           d_y[0].data_ptr(), d_y[1].data_ptr() if k == 2 else 0, mode)
+        if world > 1:
+            dist.all_reduce(d_y)                     # the path's one exchange step
+        for t in range(k):
+            ctx.sumsq_dev(d_y[t].data_ptr(), n, d_misc[t].data_ptr())
+            ctx.heritability_dev(HSQ[t], d_y[t].data_ptr(), n, d_noise[t].data_ptr(), d_misc[t].data_ptr(),
+                                 d_misc[4 + 2 * t].data_ptr())
+        if w["cc"]:
+            ctx.liability_order_dev(d_y[0].data_ptr(), n, d_index.data_ptr())
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ctx.profile_enable(True)
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    prof = {name: ctx.profile_read(i) for name, i in (("counts", 0), ("pheno_exact", 1), ("lut_main", 2),
+                                                     ("lut_build", 3), ("lut_reduce", 4))}
+    ctx.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    updates_step = n * mc * k * world
+    value = updates_step / (ms_step * 1e-3)
+    clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
+    y_check = float(d_y.abs().sum().item())
+
+    # ------------------------------------------------ e2e through the host-buffer C ABI
+    e2e_steps = max(2, min(args.steps, 5))
+    panel_view = torch.as_tensor(_DevMem(ctx.panel_ptr, (m, ctx.row_stride)), device=dev)
+    host_rows = torch.empty((mc, B), dtype=torch.uint8, pin_memory=True)
+    chunk = max(1, (1 << 30) // ctx.row_stride)
+    for lo in range(0, mc, chunk):
+        hi = min(mc, lo + chunk)
+        idx = torch.from_numpy(causal[lo:hi].astype(np.int64)).to(dev)
+        host_rows[lo:hi].copy_(panel_view.index_select(0, idx)[:, :B])
+    torch.cuda.synchronize()
+    del panel_view
+    ctx2 = capi.Context(n, device=local)
+    ctx2.panel_alloc(mc)
+    noise_h = d_noise.cpu().numpy()
+    e2e_y = None
+
+    def e2e_step():
+        nonlocal e2e_y
+        ctx2.panel_put_rows_ptr(0, mc, host_rows.data_ptr(), B)            # pinned host -> HBM, side stream
+        counts, freq = ctx2.find_freq(mc=mc)                                 # host outputs
+        y1, y2 = ctx2.find_pheno(freq, x1, x2, mode=mode)                   # host x, freq in; host y out
+        y1, _, _, _ = ctx2.apply_heritability(HSQ[0], y1, noise_h[0], None)
+        if k == 2:
+            y2, _, _, _ = ctx2.apply_heritability(HSQ[1], y2, noise_h[1], None)
+        e2e_y = (y1, y2)
+        return counts
+
+    e2e_step()
+    ctx2.sync()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx2.sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = mc * B + mc * 8 * (1 + k) + 2 * n * 8 * k
+    d2h = mc * 24 + 2 * n * 8 * k + 16 * k
+    e2e = {"value": updates_step / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "simu_b200_panel_put_rows + find_freq + find_pheno + apply_heritability (host buffers)"}
+    # the device-resident and host-buffer paths must agree (same inputs, same kernels)
+    e2e_check = float(np.abs(e2e_y[0]).sum() + (np.abs(e2e_y[1]).sum() if k == 2 else 0.0))
+
+    # ------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        probe = 64
+        rows_np = host_rows.numpy()
+        t_probe = cpu_port_time(rows_np[:probe], n, k)
+        s = int(max(probe, min(mc, 15.0 / max(t_probe / probe, 1e-7))))
+        dt = cpu_port_time(rows_np[:s], n, k)
+        cpu = {"value": n * s * k / dt, "unit": "updates/s", "cores": 1, "kind": "port",
+               "sample": f"first {s} of {mc} causal SNP rows x {n} samples, one pass ({dt:.1f} s)",
+               "host_cores": os.cpu_count()}
+
+    if rank == 0:
+        peaks, peak_src = _peaks()
+        main_key = "lut_main" if mode == capi.MODE_FAST else "pheno_exact"
+        main_ms, main_n = prof[main_key]
+        cnt_ms, cnt_n = prof["counts"]
+        roof = None
+        if main_n:
+            ach = bytes_pheno / (main_ms / main_n * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel",
+                    "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "peak_source": peak_src, "ms_per_launch": main_ms / main_n,
+                    "algorithmic_bytes_per_launch": bytes_pheno, "launches_timed": main_n}
+        counts_roof = None
+        if cnt_n:
+            ach = bytes_counts / (cnt_ms / cnt_n * 1e-3) / 1e9
+            counts_roof = {"kernel": "counts_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": ach / peaks["hbm_gbs"], "ms_per_launch": cnt_ms / cnt_n,
+                           "algorithmic_bytes_per_launch": bytes_counts}
+        line = {
+            "metric": "genotype_effect_updates_per_s", "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32-table/f64-accumulate" if mode == capi.MODE_FAST else "f64",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "desc": w["desc"], "n_samples": n, "panel_rows_per_gpu": m,
+                       "n_causal_per_gpu": mc, "traits": k, "mode": args.mode,
+                       "l2": f"inputs larger than L2 ({mc * B / 1e6:.0f} MB of causal rows per pass, 126 MB L2)",
+                       "parallelism": f"snp-shard x{world}, 1 all-reduce" if world > 1 else "single GPU"},
+            "bed_gbs": 2 * mc * B * world / (ms_step * 1e-3) / 1e9,
+            "roofline": roof, "roofline_counts": counts_roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
+            "kernel_ms": {kname: (v[0] / v[1] if v[1] else None) for kname, v in prof.items()},
+            "checksum": {"device": y_check, "e2e": e2e_check},
+        }
+        print(json.dumps(line), flush=True)
+    if sampler:
+        sampler.stop()
+    ctx2.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

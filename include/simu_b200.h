@@ -109,9 +109,9 @@ SIMU_B200_API int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, 
  * inside this file, NULL = 0..n_rows-1) are the causal rows; all others are
  * seeked past, as pio_skip_row does (bed.c:360-371).  num_loci is the .bim
  * line count.  Validates the 3-byte header (bed_header.c:80-102): returns
- * SIMU_B200_EFORMAT unless v1.00 SNP-major, SIMU_B200_END if the file holds
- * fewer than num_loci rows, SIMU_B200_ERROR if it holds more
- * (source.cc:855-858, :879-882). */
+ * SIMU_B200_EFORMAT unless v1.00 SNP-major (source.cc:196-200), SIMU_B200_END
+ * if a requested row is >= num_loci (the stream ends early, source.cc:855-858)
+ * and SIMU_B200_ERROR on a short read (bed.c:349-352 -> source.cc:226-229). */
 SIMU_B200_API int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t num_loci,
                                            const int64_t *file_rows, int64_t n_rows, int64_t dst_row);
 
@@ -179,6 +179,15 @@ SIMU_B200_API int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double
  * context, measured with CUDA events on the launching stream (kernels only;
  * 0 if none).  which: 0 = find_freq, 1 = find_pheno. */
 SIMU_B200_API int simu_b200_last_kernel_ms(simu_b200_ctx *ctx, int which, float *ms);
+
+/* Per-kernel device timing for bench.py's roofline: when enabled, every launch of the hot
+ * kernels is bracketed by a CUDA event pair on the launching stream (up to 512 pairs, then
+ * recording stops).  kernel_id: 0 = allele counts, 1 = find_pheno EXACT, 2 = find_pheno FAST
+ * main (LUT) kernel, 3 = LUT build, 4 = LUT slot reduce, 5 = sumsq/heritability, 6 = sort.
+ * profile_read synchronises the stream and returns the summed milliseconds and the number
+ * of recorded launches; profile_enable resets the record. */
+SIMU_B200_API int simu_b200_profile_enable(simu_b200_ctx *ctx, int on);
+SIMU_B200_API int simu_b200_profile_read(simu_b200_ctx *ctx, int kernel_id, float *total_ms, int *launches);
 
 #ifdef __cplusplus
 }

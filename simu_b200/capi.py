@@ -50,6 +50,8 @@ SIGNATURES = {
     "simu_b200_heritability_dev": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp, _vp]),
     "simu_b200_liability_order_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "simu_b200_last_kernel_ms": (_i32, [_vp, _i32, C.POINTER(C.c_float)]),
+    "simu_b200_profile_enable": (_i32, [_vp, _i32]),
+    "simu_b200_profile_read": (_i32, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
 }
 
 _LIB = None
@@ -133,6 +135,15 @@ class Context:
         ms = C.c_float()
         self._check(self.lib.simu_b200_last_kernel_ms(self.h, which, C.byref(ms)))
         return ms.value
+
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.simu_b200_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, kernel_id: int):
+        """-> (total_ms, launches) of the recorded launches of one kernel."""
+        ms, n = C.c_float(), C.c_int()
+        self._check(self.lib.simu_b200_profile_read(self.h, kernel_id, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # -- panel --------------------------------------------------------------
     @property

@@ -46,6 +46,27 @@ void *ctx_scratch(simu_b200_ctx *ctx, int slot, size_t bytes)
     return ctx->scratch[slot];
 }
 
+int prof_begin(simu_b200_ctx *ctx, int id)
+{
+    if (!ctx->prof_on || ctx->prof_n >= simu_b200_ctx::kProfCap) return -1;
+    if (!ctx->prof_alloc) {
+        for (int i = 0; i < simu_b200_ctx::kProfCap; i++) {
+            if (cudaEventCreate(&ctx->prof_ev[i][0]) != cudaSuccess || cudaEventCreate(&ctx->prof_ev[i][1]) != cudaSuccess)
+                return -1;
+        }
+        ctx->prof_alloc = true;
+    }
+    const int slot = ctx->prof_n++;
+    ctx->prof_id[slot] = id;
+    cudaEventRecord(ctx->prof_ev[slot][0], ctx->stream);
+    return slot;
+}
+
+void prof_end(simu_b200_ctx *ctx, int slot)
+{
+    if (slot >= 0) cudaEventRecord(ctx->prof_ev[slot][1], ctx->stream);
+}
+
 // ---------------------------------------------------------------- context
 
 extern "C" {
@@ -125,6 +146,8 @@ void simu_b200_close(simu_b200_ctx *ctx)
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
     }
+    if (ctx->prof_alloc)
+        for (int i = 0; i < simu_b200_ctx::kProfCap; i++) { cudaEventDestroy(ctx->prof_ev[i][0]); cudaEventDestroy(ctx->prof_ev[i][1]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -147,6 +170,33 @@ int simu_b200_sync(simu_b200_ctx *ctx)
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_profile_enable(simu_b200_ctx *ctx, int on)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    ctx->prof_on = on != 0;
+    ctx->prof_n = 0;
+    return SIMU_B200_OK;
+}
+
+int simu_b200_profile_read(simu_b200_ctx *ctx, int kernel_id, float *total_ms, int *launches)
+{
+    if (!ctx || !total_ms || !launches) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float tot = 0.f;
+    int n = 0;
+    for (int i = 0; i < ctx->prof_n; i++) {
+        if (ctx->prof_id[i] != kernel_id) continue;
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->prof_ev[i][0], ctx->prof_ev[i][1]));
+        tot += ms;
+        n++;
+    }
+    *total_ms = tot;
+    *launches = n;
     return SIMU_B200_OK;
 }
 

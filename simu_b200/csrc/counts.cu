@@ -120,8 +120,10 @@ int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t
     int64_t blocks = (mc + warps_per_block - 1) / warps_per_block;
     const int64_t max_blocks = (int64_t)ctx->num_sms * 8;   // 64 resident warps per SM
     if (blocks > max_blocks) blocks = max_blocks;
+    const int ps = prof_begin(ctx, PROF_COUNTS);
     counts_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>(
         ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_counts, d_freq);
+    prof_end(ctx, ps);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "counts_kernel launch");
 }

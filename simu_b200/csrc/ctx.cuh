@@ -34,6 +34,14 @@ struct simu_b200_ctx {
     void *scratch[12] = {nullptr};
     size_t scratch_bytes[12] = {0};
 
+    // optional per-kernel device timing (CUDA events on the launching stream)
+    bool prof_on = false;
+    static constexpr int kProfIds = 8, kProfCap = 512;
+    cudaEvent_t prof_ev[kProfCap][2];
+    int prof_id[kProfCap];
+    int prof_n = 0;
+    bool prof_alloc = false;
+
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
     std::string err;
@@ -53,6 +61,12 @@ void *ctx_scratch(simu_b200_ctx *ctx, int slot, size_t bytes);  // nullptr on fa
         cudaError_t _e = (expr);                                     \
         if (_e != cudaSuccess) return ctx_cuda((ctx), _e, #expr);    \
     } while (0)
+
+enum ProfId { PROF_COUNTS = 0, PROF_PHENO_EXACT = 1, PROF_LUT_MAIN = 2, PROF_LUT_BUILD = 3, PROF_LUT_REDUCE = 4,
+              PROF_REDUCTIONS = 5, PROF_SORT = 6 };
+// record a begin / end event pair around a kernel when profiling is enabled
+int prof_begin(simu_b200_ctx *ctx, int id);      // returns slot or -1
+void prof_end(simu_b200_ctx *ctx, int slot);
 
 // ---- kernel launchers (each returns a simu_b200_status) --------------------
 

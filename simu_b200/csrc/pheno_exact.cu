@@ -99,12 +99,14 @@ int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, co
                        const double *d_x1, const double *d_x2, double *d_y1, double *d_y2)
 {
     const int64_t blocks = (ctx->row_bytes + kThreads - 1) / kThreads;
+    const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
     if (d_x2 && d_y2)
         pheno_exact_kernel<2><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
             ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
     else
         pheno_exact_kernel<1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
             ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, nullptr, d_y1, nullptr);
+    prof_end(ctx, ps);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_exact_kernel launch");
 }

@@ -366,13 +366,19 @@ int run_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double 
         attr_set[K] = true;
     }
     CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
+    int ps = prof_begin(ctx, PROF_LUT_BUILD);
     lut_build_kernel<K><<<(unsigned)nblocks, 256, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, lut);
+    prof_end(ctx, ps);
 
     LutParams p;
     p.panel = ctx->panel; p.row_stride = ctx->row_stride; p.rows = d_rows; p.mc = mc; p.n_samples = n;
     p.lut = lut; p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
+    ps = prof_begin(ctx, PROF_LUT_MAIN);
     pheno_lut_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p);
+    prof_end(ctx, ps);
+    ps = prof_begin(ctx, PROF_LUT_REDUCE);
     lut_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, d_y1, d_y2);
+    prof_end(ctx, ps);
     ctx->launches += 3;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_lut launch");
 }
