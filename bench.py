@@ -293,6 +293,17 @@ def run_ours(args, w):
     clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
     y_check = float(d_y.abs().sum().item())
 
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"profiling_run": True, "ms_per_step": ms_step, "value": value,
+                              "kernel_ms": {kn: (v[0] / v[1] if v[1] else None) for kn, v in prof.items()}}), flush=True)
+        if sampler:
+            sampler.stop()
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ------------------------------------------------ e2e through the host-buffer C ABI
     e2e_steps = max(2, min(args.steps, 5))
     panel_view = torch.as_tensor(_DevMem(ctx.panel_ptr, (m, ctx.row_stride)), device=dev)
@@ -398,12 +409,13 @@ def run_ours(args, w):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

@@ -10,7 +10,7 @@
 //
 // Layout of one step (64 causal rows x 4096 samples) in a CTA:
 //   * tile: 64 rows x 1024 B in shared memory, filled by one TMA bulk copy
-//     (cp.async.bulk) per row issued by a producer warp;
+//     (cp.async.bulk) per row issued by 8 producer warps (8 rows each);
 //   * table: 16 groups (4 rows each) x 256 entries, 32 KB, precomputed once
 //     per run by lut_build_kernel in FP64 -> FP32, fetched with one bulk copy;
 //   * 8 consumer warps, 512 samples each; a lane owns one 32-bit column word
@@ -42,8 +42,10 @@ constexpr int kTableBytes = 256 * 128;               // 32 KB
 constexpr int kStageBytes = kBlockRows * kTileBytes + kTableBytes;   // 96 KB
 constexpr int kStages = 2;
 constexpr int kFlushBlocks = 64;
-constexpr int kThreads = (kWarps + 1) * 32;
-constexpr int kSmemBytes = kStages * kStageBytes + 64;
+constexpr int kProducers = 8;                        // TMA-issuing warps
+constexpr int kRowsPerProducer = kBlockRows / kProducers;
+constexpr int kThreads = (kWarps + kProducers) * 32;
+constexpr int kSmemBytes = kStages * kStageBytes + 64 + kProducers * 32 * 8;
 
 // ------------------------------------------------------------- PTX helpers
 
@@ -90,10 +92,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                  : "memory");
 }
 
@@ -173,29 +175,46 @@ __device__ __forceinline__ int64_t cta_of_step(int64_t s, int64_t grid, int64_t 
     return ((s + 1) * grid - 1) / steps;   // largest c with (c*steps)/grid <= s
 }
 
+// Accumulators are float2 so that every add is one packed FADD2 (add.f32x2, sm_100):
+//   K=2: acc[s]       = (trait1, trait2) of sample s            (16 registers pairs)
+//   K=1: acc[2*q + h] = samples (q + 8h, q + 8h + 4), q = 0..3  ( 8 register pairs)
+// The table address e*128 + base comes from ONE dot-product instruction
+// (IDP.4A: sum_i z.byte_i * sel.byte_i + base, sel = 0x80 << 8m) instead of PRMT + IMAD.
 template <int K>
-__device__ __forceinline__ void lookup4(float (&acc)[16][K], const uint32_t z, const uint32_t tbl, const int s0)
+__device__ __forceinline__ void lookup4(float2 (&acc)[8 * K], const uint32_t z, const uint32_t tbl, const int q)
 {
-    // bytes 0..3 of z are the table indices of samples s0, s0+4, s0+8, s0+12
+    // bytes 0..3 of z are the table indices of samples q, q+4, q+8, q+12
+    uint32_t a[4];
 #pragma unroll
-    for (int m = 0; m < 4; m++) {
-        const uint32_t e = __byte_perm(z, 0, 0x4440 + m);
-        const uint32_t addr = tbl + e * 128u;
-        if (K == 1) {
-            float v;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-            acc[s0 + 4 * m][0] += v;
-        } else {
-            float v0, v1;
-            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v0), "=f"(v1) : "r"(addr));
-            acc[s0 + 4 * m][0] += v0;
-            acc[s0 + 4 * m][K - 1] += v1;
+    for (int m = 0; m < 4; m++) a[m] = __dp4a(z, 0x80u << (8 * m), tbl);
+    if (K == 1) {
+        float v[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[m]) : "r"(a[m]));
+        acc[2 * q + 0] = __fadd2_rn(acc[2 * q + 0], make_float2(v[0], v[1]));
+        acc[2 * q + 1] = __fadd2_rn(acc[2 * q + 1], make_float2(v[2], v[3]));
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            float2 v;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a[m]));
+            acc[q + 4 * m] = __fadd2_rn(acc[q + 4 * m], v);
         }
     }
 }
 
+// value of (sample s, trait k) in the accumulator layout above
 template <int K>
-__device__ __forceinline__ void flush_acc(float (&acc)[16][K], double *__restrict__ ypart, int64_t npad,
+__device__ __forceinline__ float &acc_at(float2 (&acc)[8 * K], int s, int k)
+{
+    if (K == 2) return k == 0 ? acc[s].x : acc[s].y;
+    const int q = s & 3, m = s >> 2;          // s = q + 4m
+    float2 &r = acc[2 * q + (m >> 1)];
+    return (m & 1) ? r.y : r.x;
+}
+
+template <int K>
+__device__ __forceinline__ void flush_acc(float2 (&acc)[8 * K], double *__restrict__ ypart, int64_t npad,
                                           int64_t slot, int64_t sample0)
 {
 #pragma unroll
@@ -204,13 +223,13 @@ __device__ __forceinline__ void flush_acc(float (&acc)[16][K], double *__restric
 #pragma unroll
         for (int s = 0; s < 16; s += 2) {
             double2 v = *reinterpret_cast<double2 *>(dst + s);
-            v.x += (double)acc[s][k];
-            v.y += (double)acc[s + 1][k];
+            v.x += (double)acc_at<K>(acc, s, k);
+            v.y += (double)acc_at<K>(acc, s + 1, k);
             *reinterpret_cast<double2 *>(dst + s) = v;
-            acc[s][k] = 0.f;
-            acc[s + 1][k] = 0.f;
         }
     }
+#pragma unroll
+    for (int i = 0; i < 8 * K; i++) acc[i] = make_float2(0.f, 0.f);
 }
 
 template <int K>
@@ -221,6 +240,13 @@ pheno_lut_kernel(const LutParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t grid = gridDim.x, cta = blockIdx.x;
     const int64_t s_begin = (cta * p.steps) / grid, s_end = ((cta + 1) * p.steps) / grid;
+    // Every CTA walks its contiguous range in ROTATED order: at local time it, it is at the step
+    // whose row block b satisfies b == it (mod len).  All CTAs (one per sample tile for any
+    // given block) therefore need the same ~nblocks/len table blocks at the same time, so a
+    // table is fetched from HBM once and served to the other tiles' CTAs from L2.
+    const int64_t len = s_end - s_begin;
+    const int64_t rot = len > 0 ? (len - (s_begin - (s_begin / p.nblocks) * p.nblocks) % len) % len : 0;
+    auto step_at = [&](int64_t it) -> int64_t { int64_t o = it + rot; return s_begin + (o >= len ? o - len : o); };
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + kStages * kStageBytes;
@@ -228,54 +254,76 @@ pheno_lut_kernel(const LutParams p)
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; s++) {
-            mbar_init(bar_base + 8 * s, 1);
+            mbar_init(bar_base + 8 * s, kProducers);
             mbar_init(bar_base + 16 + 8 * s, kWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == kWarps) {
-        // ===================== producer warp: TMA bulk copies =====================
-        int64_t it = 0;
-        for (int64_t s = s_begin; s < s_end; s++, it++) {
+    if (warp >= kWarps) {
+        // ============ producer warps: TMA bulk copies, 32 rows of the step each ============
+        // Row sources are looked up one step ahead (the rows[] gather load is off the critical
+        // path) and published to shared memory; one lane then issues the copies back to back.
+        const int pw = warp - kWarps;
+        uint64_t pol_stream, pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        const uint8_t **ptrs = reinterpret_cast<const uint8_t **>(smem + kStages * kStageBytes + 64) + pw * 32;
+        auto row_src = [&](int64_t s) -> const uint8_t * {
+            const int64_t tile = s / p.nblocks, blk = s - tile * p.nblocks;
+            const int64_t j = blk * kBlockRows + pw * kRowsPerProducer + lane;
+            if (lane >= kRowsPerProducer || j >= p.mc) return nullptr;
+            const int64_t row = p.rows ? (int64_t)p.rows[j] : j;
+            return p.panel + row * p.row_stride + tile * kTileBytes;
+        };
+        const uint8_t *nxt = (len > 0) ? row_src(step_at(0)) : nullptr;
+        for (int64_t it = 0; it < len; it++) {
+            const int64_t s = step_at(it);
+            const uint8_t *cur = nxt;
+            if (it + 1 < len) {
+                // look up the next step's row and pull its 1 KB slice into L2 now, one whole
+                // step before its bulk copy can be issued (the stage is still being consumed)
+                const int64_t sn = step_at(it + 1);
+                nxt = row_src(sn);
+                if (nxt) {
+                    const int nlines = (int)(min((int64_t)kTileBytes, p.row_stride - (sn / p.nblocks) * kTileBytes) >> 7);
+                    for (int q = 0; q < nlines; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + q * 128));
+                }
+            }
             const int stage = (int)(it & 1);
             const uint32_t parity = (uint32_t)((it >> 1) & 1);
             const int64_t tile = s / p.nblocks, blk = s - tile * p.nblocks;
             const uint32_t full = bar_base + 8 * stage, empty = bar_base + 16 + 8 * stage;
             const uint32_t stage_base = smem_base + stage * kStageBytes;
-            const int64_t col0 = tile * kTileBytes;
-            const uint32_t bytes = (uint32_t)min((int64_t)kTileBytes, p.row_stride - col0);
-            const int64_t j0 = blk * kBlockRows;
-            const int nvalid = (int)min((int64_t)kBlockRows, p.mc - j0);
+            const uint32_t bytes = (uint32_t)min((int64_t)kTileBytes, p.row_stride - tile * kTileBytes);
+            const int nvalid = (int)max((int64_t)0, min((int64_t)kRowsPerProducer, p.mc - blk * kBlockRows - pw * kRowsPerProducer));
+            ptrs[lane] = cur;
             mbar_wait(empty, parity ^ 1u);
+            __syncwarp();
             if (lane == 0) {
-                mbar_arrive_expect_tx(full, (uint32_t)nvalid * bytes + (uint32_t)kTableBytes);
-                bulk_g2s(stage_base + kBlockRows * kTileBytes, p.lut + blk * (kTableBytes / 4), kTableBytes, full);
+                mbar_arrive_expect_tx(full, (uint32_t)nvalid * bytes + (pw == 0 ? (uint32_t)kTableBytes : 0u));
+                if (pw == 0)
+                    bulk_g2s(stage_base + kBlockRows * kTileBytes, p.lut + blk * (kTableBytes / 4), kTableBytes, full,
+                             pol_keep);
+                const uint32_t dst0 = stage_base + pw * kRowsPerProducer * kTileBytes;
+#pragma unroll 8
+                for (int r = 0; r < nvalid; r++) bulk_g2s(dst0 + r * kTileBytes, ptrs[r], bytes, full, pol_stream);
             }
             __syncwarp();
-#pragma unroll
-            for (int r = lane; r < kBlockRows; r += 32) {
-                if (r < nvalid) {
-                    const int64_t row = p.rows ? (int64_t)p.rows[j0 + r] : (j0 + r);
-                    bulk_g2s(stage_base + r * kTileBytes, p.panel + row * p.row_stride + col0, bytes, full);
-                }
-            }
         }
         return;
     }
 
     // ========================= consumer warps: lookups =========================
-    float acc[16][K];
+    float2 acc[8 * K];
 #pragma unroll
-    for (int s = 0; s < 16; s++)
-#pragma unroll
-        for (int k = 0; k < K; k++) acc[s][k] = 0.f;
+    for (int i = 0; i < 8 * K; i++) acc[i] = make_float2(0.f, 0.f);
 
-    int64_t it = 0;
     int64_t cur_tile = -1, slot = 0;
     int since_flush = 0;
-    for (int64_t s = s_begin; s < s_end; s++, it++) {
+    for (int64_t it = 0; it < len; it++) {
+        const int64_t s = step_at(it);
         const int stage = (int)(it & 1);
         const uint32_t parity = (uint32_t)((it >> 1) & 1);
         const int64_t tile = s / p.nblocks;
