@@ -58,6 +58,15 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def _traffic(workload, kernel):
+    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t[workload][kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def _causal_rows(w, rank):
     rng = np.random.default_rng(1 + rank)            # --seed 1 (+rank: each GPU owns its own slice)
     if w["mc"] == w["m"]:
@@ -374,13 +383,15 @@ def run_ours(args, w):
             ach = bytes_pheno / (main_ms / main_n * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel",
                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "peak_source": peak_src, "ms_per_launch": main_ms / main_n,
+                    "traffic": _traffic(args.workload, "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel"),
+                    "peak_source": peak_src, "ms_per_launch": main_ms / main_n,
                     "algorithmic_bytes_per_launch": bytes_pheno, "launches_timed": main_n}
         counts_roof = None
         if cnt_n:
             ach = bytes_counts / (cnt_ms / cnt_n * 1e-3) / 1e9
             counts_roof = {"kernel": "counts_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": ach / peaks["hbm_gbs"], "ms_per_launch": cnt_ms / cnt_n,
+                           "frac": ach / peaks["hbm_gbs"], "traffic": _traffic(args.workload, "counts_kernel"),
+                           "ms_per_launch": cnt_ms / cnt_n,
                            "algorithmic_bytes_per_launch": bytes_counts}
         line = {
             "metric": "genotype_effect_updates_per_s", "value": value, "unit": "updates/s", "n_gpus": world,

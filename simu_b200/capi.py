@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libsimu_b200.so")
+# SIMU_B200_LIB selects another build of the SAME library (kernel-tuning A/B runs)
+LIB_PATH = os.environ.get("SIMU_B200_LIB") or os.path.join(_PKG, "lib", "libsimu_b200.so")
 
 OK, END, ERROR, EINVAL, ECUDA, ENOMEM, EFORMAT = range(7)
 MODE_EXACT, MODE_FAST = 0, 1
