@@ -226,6 +226,7 @@ def run_ours(args, w):
         raise SystemExit("bench.py: no CUDA device; simu_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n, m, mc, k = w["n"], w["m"], w["mc"], w["k"]
@@ -334,6 +335,11 @@ def run_ours(args, w):
         ctx2.panel_put_rows_ptr(0, mc, host_rows.data_ptr(), B)            # pinned host -> HBM, side stream
         counts, freq = ctx2.find_freq(mc=mc)                                 # host outputs
         y1, y2 = ctx2.find_pheno(freq, x1, x2, mode=mode)                   # host x, freq in; host y out
+        if world > 1:                                                        # partial sums -> one all-reduce
+            t = torch.from_numpy(np.stack([y1, y2]) if k == 2 else y1[None]).to(dev)
+            dist.all_reduce(t)
+            t = t.cpu().numpy()
+            y1, y2 = t[0], (t[1] if k == 2 else None)
         y1, _, _, _ = ctx2.apply_heritability(HSQ[0], y1, noise_h[0], None)
         if k == 2:
             y2, _, _, _ = ctx2.apply_heritability(HSQ[1], y2, noise_h[1], None)

@@ -1,0 +1,195 @@
+// .bim / .fam text parsing and the concatenated fileset view, for the C++ host driver.
+//
+// Behaviour follows the reference's vendored libplinkio (paths under
+// /root/reference/libplinkio/src): fields split on runs of blanks or tabs
+// (bim_parse.c:67-71, libcsv skips leading blanks and empty lines), an integer chromosome
+// parsed with strtol and narrowed to unsigned char (bim_parse.c:112-125), float genetic and
+// long long bp positions that must parse completely (:139-175), non-empty strings
+// (:85-100), a 7th field is an error (:224-226); .fam: sex must be one character
+// (fam_parse.c:113-137), phenotype 1/2/0/-9 or a number (:149-199).  Any error makes the
+// open fail the way pio_open does: "ERROR: Could not open <prefix>" (source.cc:190-194).
+// The fileset view mirrors PioFile / PioFiles (source.cc:187-361).
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace simu {
+
+struct Locus {
+    unsigned char chromosome = 0;
+    std::string name;
+    float position = 0.f;
+    long long bp_position = 0;
+    std::string allele1, allele2;
+};
+
+struct Sample {
+    std::string fid, iid;
+};
+
+inline std::vector<std::string> split_blank(const std::string &line)
+{
+    std::vector<std::string> out;
+    size_t i = 0;
+    const size_t n = line.size();
+    while (i < n) {
+        while (i < n && (line[i] == ' ' || line[i] == '\t' || line[i] == '\r')) i++;
+        size_t j = i;
+        while (j < n && line[j] != ' ' && line[j] != '\t' && line[j] != '\r') j++;
+        if (j > i) out.emplace_back(line, i, j - i);
+        i = j;
+    }
+    return out;
+}
+
+inline bool full_long(const std::string &s, long long *v)
+{
+    char *end = nullptr;
+    *v = strtoll(s.c_str(), &end, 10);
+    return !s.empty() && end && *end == '\0';
+}
+
+inline bool full_double(const std::string &s, double *v)
+{
+    char *end = nullptr;
+    *v = strtod(s.c_str(), &end);
+    return !s.empty() && end && *end == '\0';
+}
+
+inline bool parse_bim_file(const std::string &path, std::vector<Locus> *loci)
+{
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        std::vector<std::string> t = split_blank(line);
+        if (t.empty()) continue;
+        if (t.size() > 6) return false;
+        Locus l;
+        long long v;
+        double d;
+        // rows with fewer than six fields are kept with defaults, as libplinkio's new_row does
+        if (t.size() > 0) { if (!full_long(t[0], &v)) return false; l.chromosome = (unsigned char)v; }
+        if (t.size() > 1) l.name = t[1];
+        if (t.size() > 2) { if (!full_double(t[2], &d)) return false; l.position = (float)d; }
+        if (t.size() > 3) { if (!full_long(t[3], &v)) return false; l.bp_position = v; }
+        if (t.size() > 4) l.allele1 = t[4];
+        if (t.size() > 5) l.allele2 = t[5];
+        loci->push_back(std::move(l));
+    }
+    return true;
+}
+
+inline bool parse_fam_file(const std::string &path, std::vector<Sample> *samples)
+{
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        std::vector<std::string> t = split_blank(line);
+        if (t.empty()) continue;
+        if (t.size() > 6) return false;
+        if (t.size() > 4 && t[4].size() != 1) return false;                 // parse_sex
+        if (t.size() > 5) {                                                  // parse_phenotype
+            double d;
+            const std::string &p = t[5];
+            const bool code = p.size() == 1 && (p[0] == '0' || p[0] == '1' || p[0] == '2');
+            const bool miss = strncmp(p.c_str(), "-9", p.size()) == 0;
+            if (!code && !miss && !full_double(p, &d)) return false;
+        }
+        Sample s;
+        s.fid = t[0];
+        if (t.size() > 1) s.iid = t[1];
+        samples->push_back(std::move(s));
+    }
+    return true;
+}
+
+// One bfile prefix (PioFile, source.cc:187-267).
+struct PlinkFile {
+    std::string prefix;
+    std::vector<Locus> loci;
+    std::vector<Sample> samples;
+
+    explicit PlinkFile(const std::string &bfile) : prefix(bfile)
+    {
+        const std::string fail = "ERROR: Could not open " + bfile;
+        if (!parse_fam_file(bfile + ".fam", &samples)) throw std::runtime_error(fail);
+        if (!parse_bim_file(bfile + ".bim", &loci)) throw std::runtime_error(fail);
+        FILE *fp = fopen((bfile + ".bed").c_str(), "rb");
+        if (!fp) throw std::runtime_error(fail);
+        unsigned char h[3];
+        const size_t got = fread(h, 1, 3, fp);
+        fclose(fp);
+        if (got != 3) throw std::runtime_error(fail);                      // bed.c:52-58
+        const bool v100 = h[0] == 0x6c && h[1] == 0x1b;                     // bed_header.c:80-102
+        const bool snp_major = v100 ? (h[2] == 0x01) : false;
+        if (!snp_major)                                                     // source.cc:196-200
+            throw std::runtime_error("ERROR: Unsupported format in " + bfile +
+                                     ", snps must be rows, samples must be columns");
+        if (samples.empty())                                                // source.cc:202-206
+            throw std::runtime_error("ERROR: Unsupported format in " + bfile + ", rows appears to have zero size");
+    }
+    int num_samples() const { return (int)samples.size(); }
+    int num_loci() const { return (int)loci.size(); }
+};
+
+// Concatenation in label order (PioFiles, source.cc:269-361).
+class PlinkFiles {
+public:
+    void push_back(PlinkFile &&f)
+    {
+        offsets_.push_back(num_variants_);
+        num_variants_ += f.num_loci();
+        files_.push_back(std::move(f));
+    }
+    int num_variants() const { return num_variants_; }
+    size_t num_files() const { return files_.size(); }
+    const PlinkFile &file(size_t i) const { return files_[i]; }
+    int offset(size_t i) const { return offsets_[i]; }
+    const Sample &get_sample(size_t i) const { return files_[0].samples[i]; }     // source.cc:309-311
+    const Locus *get_locus(int variant_index) const                                // source.cc:313-320
+    {
+        for (size_t i = 0; i < files_.size(); i++) {
+            if (variant_index < files_[i].num_loci()) return &files_[i].loci[variant_index];
+            variant_index -= files_[i].num_loci();
+        }
+        return nullptr;
+    }
+    void find_variant_index_map()                                                  // source.cc:327-343
+    {
+        if (!snp_to_id_.empty())
+            throw std::runtime_error("internal error - find_variant_index_map must be called once");
+        for (int v = 0; v < num_variants_; v++) {
+            const Locus *l = get_locus(v);
+            if (!snp_to_id_.insert({l->name, v}).second)
+                throw std::runtime_error("ERROR: duplicated variant name: " + l->name);
+        }
+    }
+    int get_locus_id(const std::string &name) const                                // source.cc:345-352
+    {
+        auto it = snp_to_id_.find(name);
+        if (it == snp_to_id_.end())
+            throw std::runtime_error("ERROR: locus with name " + name +
+                                     " does not exist in the input; check your --bfile and/or --causal-variants, "
+                                     "--causal-regions arguments");
+        return it->second;
+    }
+
+private:
+    std::vector<PlinkFile> files_;
+    std::vector<int> offsets_;
+    std::map<std::string, int> snp_to_id_;
+    int num_variants_ = 0;
+};
+
+}  // namespace simu

@@ -1,0 +1,175 @@
+"""The drop-in CLI end to end on a B200 against a Python restatement of the
+reference pipeline (/root/reference/src/source.cc:1222-1316) built from the CPU
+oracle (hot path) and tests/pyrng.py (draw order of SURVEY.md 9.2).
+
+.pheno / .causals are text at 6 significant digits (source.cc:1066, :1101-1103),
+so numbers are compared after parsing, at 2e-5 relative (1e-5 for FAST mode + print
+rounding); case/control labels must agree exactly away from threshold ties.
+"""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import pyrng  # noqa: E402
+from oracle import oracle  # noqa: E402
+from simu_b200 import plink  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "simu_b200", "bin", "simu_b200")
+F32 = np.float32
+
+
+def run(args, cwd, mode="fast"):
+    env = dict(os.environ, SIMU_B200_MODE=mode)
+    p = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+def read_table(path):
+    rows = [l.rstrip("\n").split("\t") for l in open(path)]
+    return rows[0], rows[1:]
+
+
+def close(a, b, rtol=1e-5):
+    """|a-b| <= 1e-5 * max|b| (the FAST-mode bound, relative to the vector's scale)
+    + 6-significant-digit print rounding of each number."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.all(np.abs(a - b) <= rtol * np.max(np.abs(b)) + 6e-6 * np.abs(b) + 1e-12)
+
+
+def expected_pipeline(rows, n, m, seed, num_traits=1, causal_n=50, hsq=(0.7, 0.7), rg=0.0, gcta=False, cc=False, k=0.1):
+    """source.cc:1222-1306 with the oracle as the hot path."""
+    rng = pyrng.Mt19937(seed)
+    perm = pyrng.random_shuffle(list(range(m)), rng)                     # :829-831
+    comp = np.full(m, -1)
+    comp[perm[:causal_n]] = 0                                            # :833-838
+    causal = np.flatnonzero(comp != -1)
+    _, freq = oracle.find_freq(rows, n, row_index=causal)                # :1235
+    normal = pyrng.NormalDraws(rng)                                      # :894 / :937
+    x1 = np.zeros(causal.size); x2 = np.zeros(causal.size)
+    for j in range(causal.size):                                         # ascending variant index
+        if num_traits == 1:
+            x1[j] = math.sqrt(float(F32(1.0))) * normal()
+        else:
+            a, b = normal(), normal()
+            r = float(F32(rg))
+            x1[j] = a
+            x2[j] = r * a + math.sqrt(1 - r * r) * b
+    if gcta:                                                             # :1245-1264
+        het = np.abs(2 * freq * (1 - freq))
+        x1 *= np.sqrt(het ** -1.0)
+        x2 *= np.sqrt(het ** -1.0)
+    y1, y2 = oracle.find_pheno(rows, n, freq, x1, x2 if num_traits == 2 else None, row_index=causal)   # :1295
+    ys, xs = [y1, y2][:num_traits], [x1, x2][:num_traits]
+    for t in range(num_traits):                                          # :1299-1300 (noise: N draws per trait)
+        normal = pyrng.NormalDraws(rng)
+        noise = np.array([normal() for _ in range(n)])
+        ys[t], xs[t], _, _ = oracle.apply_heritability(float(F32(hsq[t])), ys[t], noise, xs[t])
+    if cc:                                                               # :1303-1306
+        for t in range(num_traits):
+            idx = oracle.liability_order(ys[t])
+            max_cas, max_con = oracle.liability_split(float(F32(k)), n)
+            con = pyrng.random_shuffle(list(range(max_con)), rng)
+            cas = pyrng.random_shuffle(list(range(max_con, n)), rng)
+            ys[t] = oracle.liability_labels(float(F32(k)), max_cas, n - max_cas, idx, con, cas)
+    return causal, freq, xs, ys
+
+
+@pytest.fixture(scope="module")
+def fileset(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cli")
+    n, m = 1203, 900
+    rows = oracle.synth_rows(20240901, 0, m, n)
+    plink.write_fileset(str(d / "syn"), rows, n)
+    return d, rows, n, m
+
+
+@pytest.mark.parametrize("mode", ["fast", "exact"])
+def test_qt_single_trait(fileset, mode):
+    d, rows, n, m = fileset
+    out = run(["--bfile", "syn", "--qt", "--causal-n", "50", "--hsq", "0.5", "--seed", "1", "--out", f"qt_{mode}"], d, mode)
+    assert "Calculate allele frequencies (for causal markers only)..." in out and "Calculate phenotypes..." in out
+    causal, freq, xs, ys = expected_pipeline(rows, n, m, 1, causal_n=50, hsq=(0.5,))
+    hdr, body = read_table(d / f"qt_{mode}.pheno")
+    assert hdr == ["FID", "IID", "trait1"] and len(body) == n
+    assert body[0][:2] == ["id1_0", "id2_0"] and body[-1][:2] == [f"id1_{n-1}", f"id2_{n-1}"]
+    assert close([r[2] for r in body], ys[0])
+    hdr, body = read_table(d / f"qt_{mode}.1.causals")
+    assert hdr == ["SNP", "CHR", "POS", "A1", "A2", "FRQ", "BETA_c1"]
+    assert [r[0] for r in body] == [f"rs{v}" for v in causal]
+    assert [r[1:5] for r in body[:1]] == [["1", str(causal[0] + 1), "A", "G"]]
+    assert close([r[5] for r in body], freq) and close([r[6] for r in body], xs[0])
+
+
+def test_two_traits_gcta_norm_effect(fileset):
+    d, rows, n, m = fileset
+    run(["--bfile", "syn", "--qt", "--num-traits", "2", "--rg", "0.5", "--gcta-sigma", "--norm-effect", "--causal-n", "120",
+         "--hsq", "0.5", "0.3", "--seed", "7", "--out", "biv"], d)
+    causal, freq, xs, ys = expected_pipeline(rows, n, m, 7, num_traits=2, causal_n=120, hsq=(0.5, 0.3), rg=0.5, gcta=True)
+    hdr, body = read_table(d / "biv.pheno")
+    assert hdr == ["FID", "IID", "trait1", "trait2"]
+    assert close([r[2] for r in body], ys[0]) and close([r[3] for r in body], ys[1])
+    het = np.abs(2 * freq * (1 - freq))
+    for t in (0, 1):                                                     # --norm-effect: beta * sqrt(het) (source.cc:1090-1094)
+        _, body = read_table(d / f"biv.{t+1}.causals")
+        assert close([r[6] for r in body], xs[t] * np.sqrt(het))
+
+
+def test_case_control_labels(fileset):
+    d, rows, n, m = fileset
+    run(["--bfile", "syn", "--cc", "--k", "0.1", "--causal-n", "80", "--seed", "3", "--out", "cc"], d, "exact")
+    _, _, _, ys = expected_pipeline(rows, n, m, 3, causal_n=80, hsq=(0.7,), cc=True, k=0.1)
+    _, body = read_table(d / "cc.pheno")
+    got = np.array([float(r[2]) for r in body])
+    assert set(np.unique(got)) <= {1.0, 2.0}
+    assert np.count_nonzero(got == 2) == int(math.floor(float(F32(0.1) * F32(n))))
+    assert np.array_equal(got, ys[0])                                    # no ties at the threshold in this panel
+
+
+def test_causal_variants_file_with_effects(fileset):
+    """--causal-variants with effect sizes, --hsq 1 (env_coef = 0: no dependence on the noise draws)."""
+    d, rows, n, m = fileset
+    rng = np.random.default_rng(0)
+    sel = np.sort(rng.choice(m, 40, replace=False))
+    b1, b2 = rng.standard_normal(40), rng.standard_normal(40)
+    with open(d / "causal.txt", "w") as f:
+        for v, a, b in zip(sel, b1, b2):
+            f.write(f"rs{v}\t{float(a)!r}\t{float(b)!r}\n")
+    out = run(["--bfile", "syn", "--qt", "--num-traits", "2", "--causal-variants", "causal.txt", "--hsq", "1", "1", "--seed", "9",
+               "--out", "cv"], d, "exact")
+    assert "Use effect sizes provided in --causal-variants file." in out
+    _, freq = oracle.find_freq(rows, n, row_index=sel)
+    y1, y2 = oracle.find_pheno(rows, n, freq, b1, b2, row_index=sel)
+    e1, _, g1, _ = oracle.apply_heritability(1.0, y1, np.zeros(n), None)
+    e2, _, g2, _ = oracle.apply_heritability(1.0, y2, np.zeros(n), None)
+    _, body = read_table(d / "cv.pheno")
+    assert close([r[2] for r in body], e1) and close([r[3] for r in body], e2)
+    _, body = read_table(d / "cv.2.causals")
+    assert [r[0] for r in body] == [f"rs{v}" for v in sel] and close([r[6] for r in body], b2 * g2)
+
+
+def test_bfile_chr_concatenation(tmp_path):
+    n = 301
+    sizes = {"1": 40, "2": 25, "3": 35}
+    rows = oracle.synth_rows(20240901, 0, sum(sizes.values()), n)
+    off = 0
+    for lab, sz in sizes.items():
+        plink.write_fileset(str(tmp_path / f"c{lab}"), rows[off:off + sz], n, chromosome=int(lab), first_index=off)
+        off += sz
+    out = run(["--bfile-chr", "c@", "--chr-labels", "1", "2", "3", "--qt", "--causal-pi", "0.3", "--seed", "11", "--out", "chr"],
+              tmp_path, "exact")
+    assert "Found 100 variants in total." in out
+    causal, freq, xs, ys = expected_pipeline(rows, n, 100, 11, causal_n=int(F32(0.3) * 100), hsq=(0.7,))
+    _, body = read_table(tmp_path / "chr.pheno")
+    assert close([r[2] for r in body], ys[0])
+    _, body = read_table(tmp_path / "chr.1.causals")
+    chrom = lambda v: "1" if v < 40 else ("2" if v < 65 else "3")     # noqa: E731
+    assert [(r[0], r[1]) for r in body] == [(f"rs{v}", chrom(v)) for v in causal]
