@@ -17,7 +17,7 @@
 //     tables cannot be restated here; draws against such a build are NOT pinned.
 //   * std::random_shuffle(first, last, rand): libstdc++'s loop
 //     (for i in 1..n-1: j = rand(i+1); if i != j swap).
-// Hot-path parity does not depend on any of this: the oracle and the GPU path consume the
+// Hot-path parity does not depend on any of this: the CPU checker and the GPU path consume the
 // same x and e.
 #pragma once
 
