@@ -92,6 +92,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     }
 }
 
+// Producer-side wait: poll with back-off so that the waiting warp does not burn issue slots
+// the consumer warps need (the bare try_wait loop was 35 % of all executed instructions).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
+{
+    if (mbar_test(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_test(bar, parity)) {
+        __nanosleep(100);
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -246,7 +258,20 @@ pheno_lut_kernel(const LutParams p)
     // table is fetched from HBM once and served to the other tiles' CTAs from L2.
     const int64_t len = s_end - s_begin;
     const int64_t rot = len > 0 ? (len - (s_begin - (s_begin / p.nblocks) * p.nblocks) % len) % len : 0;
-    auto step_at = [&](int64_t it) -> int64_t { int64_t o = it + rot; return s_begin + (o >= len ? o - len : o); };
+    // (tile, block) of the current step are carried along incrementally: 64-bit divisions
+    // cost ~100 instructions each and used to be a quarter of all issued instructions.
+    const int64_t nb = p.nblocks;
+    const int64_t tile_b = s_begin / nb, blk_b = s_begin - tile_b * nb;
+    struct Cursor { int64_t s, tile, blk; };
+    Cursor first;
+    first.s = s_begin + rot;
+    first.tile = tile_b + (blk_b + rot) / nb;
+    first.blk = (blk_b + rot) - (first.tile - tile_b) * nb;
+    auto advance = [&](Cursor &c) {
+        c.s++; c.blk++;
+        if (c.blk == nb) { c.blk = 0; c.tile++; }
+        if (c.s == s_end) { c.s = s_begin; c.tile = tile_b; c.blk = blk_b; }
+    };
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + kStages * kStageBytes;
@@ -270,37 +295,38 @@ pheno_lut_kernel(const LutParams p)
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
         const uint8_t **ptrs = reinterpret_cast<const uint8_t **>(smem + kStages * kStageBytes + 64) + pw * 32;
-        auto row_src = [&](int64_t s) -> const uint8_t * {
-            const int64_t tile = s / p.nblocks, blk = s - tile * p.nblocks;
-            const int64_t j = blk * kBlockRows + pw * kRowsPerProducer + lane;
+        auto row_src = [&](const Cursor &c) -> const uint8_t * {
+            const int64_t j = c.blk * kBlockRows + pw * kRowsPerProducer + lane;
             if (lane >= kRowsPerProducer || j >= p.mc) return nullptr;
             const int64_t row = p.rows ? (int64_t)p.rows[j] : j;
-            return p.panel + row * p.row_stride + tile * kTileBytes;
+            return p.panel + row * p.row_stride + c.tile * kTileBytes;
         };
-        const uint8_t *nxt = (len > 0) ? row_src(step_at(0)) : nullptr;
+        Cursor cn = first;                              // cursor of the step being looked up ahead
+        const uint8_t *nxt = (len > 0) ? row_src(cn) : nullptr;
         for (int64_t it = 0; it < len; it++) {
-            const int64_t s = step_at(it);
+            const int64_t tile = cn.tile, blk = cn.blk;
             const uint8_t *cur = nxt;
             if (it + 1 < len) {
                 // look up the next step's row and pull its 1 KB slice into L2 now, one whole
                 // step before its bulk copy can be issued (the stage is still being consumed)
-                const int64_t sn = step_at(it + 1);
-                nxt = row_src(sn);
+                advance(cn);
+                nxt = row_src(cn);
                 if (nxt) {
-                    const int nlines = (int)(min((int64_t)kTileBytes, p.row_stride - (sn / p.nblocks) * kTileBytes) >> 7);
+                    const int nlines = (int)(min((int64_t)kTileBytes, p.row_stride - cn.tile * kTileBytes) >> 7);
                     for (int q = 0; q < nlines; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + q * 128));
                 }
             }
             const int stage = (int)(it & 1);
             const uint32_t parity = (uint32_t)((it >> 1) & 1);
-            const int64_t tile = s / p.nblocks, blk = s - tile * p.nblocks;
             const uint32_t full = bar_base + 8 * stage, empty = bar_base + 16 + 8 * stage;
             const uint32_t stage_base = smem_base + stage * kStageBytes;
             const uint32_t bytes = (uint32_t)min((int64_t)kTileBytes, p.row_stride - tile * kTileBytes);
             const int nvalid = (int)max((int64_t)0, min((int64_t)kRowsPerProducer, p.mc - blk * kBlockRows - pw * kRowsPerProducer));
             ptrs[lane] = cur;
-            mbar_wait(empty, parity ^ 1u);
-            __syncwarp();
+            // one warp polls the mbarrier; the other producer warps sleep in a named hardware
+            // barrier until it gets through (bar.sync also orders the ptrs[] stores)
+            if (pw == 0) mbar_wait_backoff(empty, parity ^ 1u);
+            asm volatile("bar.sync 1, %0;" ::"n"(kProducers * 32) : "memory");
             if (lane == 0) {
                 mbar_arrive_expect_tx(full, (uint32_t)nvalid * bytes + (pw == 0 ? (uint32_t)kTableBytes : 0u));
                 if (pw == 0)
@@ -322,11 +348,11 @@ pheno_lut_kernel(const LutParams p)
 
     int64_t cur_tile = -1, slot = 0;
     int since_flush = 0;
-    for (int64_t it = 0; it < len; it++) {
-        const int64_t s = step_at(it);
+    Cursor cc = first;
+    for (int64_t it = 0; it < len; it++, advance(cc)) {
         const int stage = (int)(it & 1);
         const uint32_t parity = (uint32_t)((it >> 1) & 1);
-        const int64_t tile = s / p.nblocks;
+        const int64_t tile = cc.tile;
         if (tile != cur_tile || since_flush == kFlushBlocks) {
             if (cur_tile >= 0)
                 flush_acc<K>(acc, p.ypart, p.npad, slot, cur_tile * kTileSamples + warp * 512 + lane * 16);
