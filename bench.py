@@ -200,7 +200,7 @@ def run_reference(args, w):
         "gpu_launches": 0,
         "bed_gbs": s * ((n + 3) // 4) * 2 / dt / 1e9,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ our arm
@@ -305,8 +305,8 @@ def run_ours(args, w):
 
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"profiling_run": True, "ms_per_step": ms_step, "value": value,
-                              "kernel_ms": {kn: (v[0] / v[1] if v[1] else None) for kn, v in prof.items()}}), flush=True)
+            emit({"profiling_run": True, "ms_per_step": ms_step, "value": value,
+                  "kernel_ms": {kn: (v[0] / v[1] if v[1] else None) for kn, v in prof.items()}})
         if sampler:
             sampler.stop()
         ctx.close()
@@ -414,7 +414,7 @@ def run_ours(args, w):
             "kernel_ms": {kname: (v[0] / v[1] if v[1] else None) for kname, v in prof.items()},
             "checksum": {"device": y_check, "e2e": e2e_check},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if sampler:
         sampler.stop()
     ctx2.close()
@@ -423,7 +423,29 @@ def run_ours(args, w):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: route everything any library writes to fd 1
+    (NCCL's version banner, torchrun notices) to stderr and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)

@@ -144,6 +144,9 @@ void simu_b200_close(simu_b200_ctx *ctx)
     for (int i = 0; i < 12; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->dstage[i]) cudaFree(ctx->dstage[i]);
+        if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
+        if (ctx->ev_repitch[i]) cudaEventDestroy(ctx->ev_repitch[i]);
         if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
     }
     if (ctx->prof_alloc)
@@ -247,6 +250,38 @@ static int ensure_pinned(simu_b200_ctx *ctx)
     return SIMU_B200_OK;
 }
 
+static int ensure_dstage(simu_b200_ctx *ctx)
+{
+    for (int i = 0; i < 2; i++) {
+        if (!ctx->dstage[i]) {
+            cudaError_t e = cudaMalloc((void **)&ctx->dstage[i], SIMU_STAGE_BYTES);
+            if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaMalloc(device staging)");
+        }
+        if (!ctx->ev_copy[i]) {
+            cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_repitch[i], cudaEventDisableTiming);
+            if (e != cudaSuccess) return ctx_cuda(ctx, e, "staging events");
+        }
+    }
+    return SIMU_B200_OK;
+}
+
+// One chunk of contiguous packed rows (page-locked host memory) -> panel rows:
+// 1-D DMA on the copy stream into bounce buffer `buf`, re-pitch kernel on the compute stream.
+static int stage_chunk(simu_b200_ctx *ctx, const uint8_t *pinned_src, int64_t nr, int64_t dst_row, int buf)
+{
+    if (ctx->dstage_used[buf]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_repitch[buf], 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dstage[buf], pinned_src, (size_t)(nr * ctx->row_bytes), cudaMemcpyHostToDevice,
+                                  ctx->copy_stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
+    int rc = launch_repitch(ctx, ctx->dstage[buf], nr, dst_row, ctx->stream);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_repitch[buf], ctx->stream));
+    ctx->dstage_used[buf] = true;
+    return SIMU_B200_OK;
+}
+
 static int check_rows(simu_b200_ctx *ctx, const char *who, int64_t first, int64_t n)
 {
     if (!ctx->panel) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: no panel allocated", who);
@@ -289,9 +324,18 @@ int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows
     bool is_pinned = (cudaPointerGetAttributes(&attr, host_rows) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     const uint8_t *src = (const uint8_t *)host_rows;
+    if (is_pinned && host_stride == ctx->row_bytes) {
+        // page-locked and contiguous: chunked 1-D DMA straight from the caller's buffer into the
+        // device bounce buffers, re-pitched on the compute stream while the next chunk copies
+        if ((rc = ensure_dstage(ctx))) return rc;
+        const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
+        int buf = 0;
+        for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1)
+            if ((rc = stage_chunk(ctx, src + r * host_stride, std::min(rows_per, n_rows - r), dst_row + r, buf))) return rc;
+        return SIMU_B200_OK;      // the compute stream is already ordered behind the last re-pitch
+    }
     if (is_pinned) {
-        // already page-locked: DMA straight from the caller's buffer, in chunks so that the
-        // copy engine pipeline stays short-queued
+        // page-locked but strided: pitched 2-D DMA from the caller's buffer
         const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
         for (int64_t r = 0; r < n_rows; r += rows_per) {
             const int64_t nr = std::min(rows_per, n_rows - r);
@@ -300,25 +344,24 @@ int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows
                                             (size_t)nr, cudaMemcpyHostToDevice, ctx->copy_stream));
         }
     } else {
-        if ((rc = ensure_pinned(ctx))) return rc;
+        if ((rc = ensure_pinned(ctx)) || (rc = ensure_dstage(ctx))) return rc;
         const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
         int buf = 0;
         bool used[2] = {false, false};
         for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1) {
             const int64_t nr = std::min(rows_per, n_rows - r);
-            if (used[buf]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_stage[buf]));
+            if (ctx->dstage_used[buf]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_copy[buf]));   // DMA out of pinned[buf] done
             if (host_stride == ctx->row_bytes) {
                 memcpy(ctx->pinned[buf], src + r * host_stride, (size_t)(nr * ctx->row_bytes));
             } else {
                 for (int64_t q = 0; q < nr; q++)
                     memcpy(ctx->pinned[buf] + q * ctx->row_bytes, src + (r + q) * host_stride, (size_t)ctx->row_bytes);
             }
-            CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->panel + (dst_row + r) * ctx->row_stride, (size_t)ctx->row_stride,
-                                            ctx->pinned[buf], (size_t)ctx->row_bytes, (size_t)ctx->row_bytes,
-                                            (size_t)nr, cudaMemcpyHostToDevice, ctx->copy_stream));
-            CUDA_TRY(ctx, cudaEventRecord(ctx->ev_stage[buf], ctx->copy_stream));
+            if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + r, buf))) return rc;
             used[buf] = true;
         }
+        // the caller may free or reuse host_rows on return; pinned[] is ours, nothing to wait for
+        return SIMU_B200_OK;
     }
     return join_copy_stream(ctx);
 }
@@ -367,7 +410,7 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
                         "ERROR: Unsupported format in %s, snps must be rows, samples must be columns", bed_path);
     }
     if (n_rows == 0) { close(fd); return SIMU_B200_OK; }
-    if ((rc = ensure_pinned(ctx)) || (rc = fork_copy_stream(ctx))) { close(fd); return rc; }
+    if ((rc = ensure_pinned(ctx)) || (rc = ensure_dstage(ctx)) || (rc = fork_copy_stream(ctx))) { close(fd); return rc; }
 
     const int64_t B = ctx->row_bytes;
     const int64_t cap_rows = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / B);
@@ -376,8 +419,8 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
     int64_t done = 0, prev = -1;
     while (done < n_rows) {
         const int64_t nr = std::min(cap_rows, n_rows - done);
-        if (used[buf]) {
-            cudaError_t e = cudaEventSynchronize(ctx->ev_stage[buf]);
+        if (ctx->dstage_used[buf]) {
+            cudaError_t e = cudaEventSynchronize(ctx->ev_copy[buf]);      // DMA out of pinned[buf] done
             if (e != cudaSuccess) { close(fd); return ctx_cuda(ctx, e, "staging event sync"); }
         }
         // coalesce runs of adjacent causal rows into single preads (pio_skip_row defers the
@@ -406,19 +449,15 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
             prev = r0 + run - 1;
             q += run;
         }
-        cudaError_t e = cudaMemcpy2DAsync(ctx->panel + (dst_row + done) * ctx->row_stride, (size_t)ctx->row_stride,
-                                          ctx->pinned[buf], (size_t)B, (size_t)B, (size_t)nr, cudaMemcpyHostToDevice,
-                                          ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_stage[buf], ctx->copy_stream);
-        if (e != cudaSuccess) { close(fd); return ctx_cuda(ctx, e, "staging copy"); }
+        if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + done, buf))) { close(fd); return rc; }
         used[buf] = true;
         buf ^= 1;
         done += nr;
     }
     close(fd);
-    // the staging buffers are reused by the next call: drain before returning
+    // the pinned buffers are reused by the next call: drain the DMA queue before returning
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    return join_copy_stream(ctx);
+    return SIMU_B200_OK;
 }
 
 int simu_b200_panel_synth(simu_b200_ctx *ctx, uint64_t panel_seed, int64_t first_row, int64_t n_rows,

@@ -29,6 +29,9 @@ struct simu_b200_ctx {
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint8_t *pinned[2] = {nullptr, nullptr};
+    uint8_t *dstage[2] = {nullptr, nullptr};            // device bounce buffers for 1-D staging
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_repitch[2] = {nullptr, nullptr};
+    bool dstage_used[2] = {false, false};
 
     // grow-on-demand device scratch
     void *scratch[12] = {nullptr};
@@ -86,6 +89,9 @@ int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out
 int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
                         const double *d_sumsq, double *d_coef);
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index);
+
+// staging: re-base contiguous rows to the panel pitch.  stage.cu
+int launch_repitch(simu_b200_ctx *ctx, const uint8_t *d_src, int64_t n_rows, int64_t dst_row, cudaStream_t stream);
 
 // synthetic panel generator.  synth.cu
 int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, int64_t n_rows, int64_t dst_row);

@@ -173,3 +173,71 @@ def test_bfile_chr_concatenation(tmp_path):
     _, body = read_table(tmp_path / "chr.1.causals")
     chrom = lambda v: "1" if v < 40 else ("2" if v < 65 else "3")     # noqa: E731
     assert [(r[0], r[1]) for r in body] == [(f"rs{v}", chrom(v)) for v in causal]
+
+
+def test_causal_regions_and_components(fileset):
+    """--causal-regions with two mixture components: one shuffle per region file
+    (source.cc:816-826), effects drawn in ascending variant order with per-component sigsq."""
+    d, rows, n, m = fileset
+    reg = [list(range(10, 200)), list(range(400, 650))]
+    for c, r in enumerate(reg):
+        with open(d / f"region{c}.txt", "w") as f:
+            f.write("\n".join(f"rs{v}" for v in r) + "\n")
+    run(["--bfile", "syn", "--qt", "--num-components", "2", "--causal-n", "20", "30", "--causal-regions", "region0.txt",
+         "region1.txt", "--trait1-sigsq", "1", "0.25", "--hsq", "0.6", "--seed", "21", "--out", "reg"], d, "exact")
+    rng = pyrng.Mt19937(21)
+    comp = np.full(m, -1)
+    for c, (r, k) in enumerate(zip(reg, (20, 30))):
+        idx = pyrng.random_shuffle(list(r), rng)
+        comp[idx[:k]] = c
+    causal = np.flatnonzero(comp != -1)
+    _, freq = oracle.find_freq(rows, n, row_index=causal)
+    normal = pyrng.NormalDraws(rng)
+    sig = [math.sqrt(float(F32(1.0))), math.sqrt(float(F32(0.25)))]
+    x = np.array([sig[comp[v]] * normal() for v in causal])
+    y, _ = oracle.find_pheno(rows, n, freq, x, None, row_index=causal)
+    normal = pyrng.NormalDraws(rng)
+    noise = np.array([normal() for _ in range(n)])
+    y, x, _, _ = oracle.apply_heritability(float(F32(0.6)), y, noise, x)
+    _, body = read_table(d / "reg.pheno")
+    assert close([r[2] for r in body], y)
+    hdr, body = read_table(d / "reg.1.causals")
+    assert hdr[-2:] == ["BETA_c1", "BETA_c2"]
+    assert [r[0] for r in body] == [f"rs{v}" for v in causal]
+    got = np.array([[float(r[6]), float(r[7])] for r in body])
+    exp = np.zeros_like(got)
+    exp[np.arange(causal.size), comp[causal]] = x
+    assert close(got.ravel(), exp.ravel())
+
+
+def test_trait2_snp_offset(fileset):
+    """--trait2-snp-offset: three implicit components (source.cc:691-695, :731-757, :903-924)."""
+    d, rows, n, m = fileset
+    run(["--bfile", "syn", "--qt", "--num-traits", "2", "--causal-n", "40", "--trait2-snp-offset", "1", "--hsq", "0.5", "0.5",
+         "--seed", "33", "--out", "off"], d, "exact")
+    rng = pyrng.Mt19937(33)
+    perm = pyrng.random_shuffle(list(range(m)), rng)
+    comp = np.full(m, -1)
+    for s1 in perm[:40]:
+        comp[s1] += 1
+        comp[(s1 + 1) % m] += 2
+    causal = np.flatnonzero(comp != -1)
+    _, freq = oracle.find_freq(rows, n, row_index=causal)
+    normal = pyrng.NormalDraws(rng)
+    x1 = np.zeros(causal.size); x2 = np.zeros(causal.size)
+    for j, v in enumerate(causal):
+        a, b = normal(), normal()
+        if comp[v] in (0, 2):
+            x1[j] = a
+        if comp[v] in (1, 2):
+            x2[j] = b
+    y1, y2 = oracle.find_pheno(rows, n, freq, x1, x2, row_index=causal)
+    out = []
+    for y, x in ((y1, x1), (y2, x2)):
+        normal = pyrng.NormalDraws(rng)
+        noise = np.array([normal() for _ in range(n)])
+        out.append(oracle.apply_heritability(float(F32(0.5)), y, noise, x))
+    _, body = read_table(d / "off.pheno")
+    assert close([r[2] for r in body], out[0][0]) and close([r[3] for r in body], out[1][0])
+    hdr, body = read_table(d / "off.2.causals")
+    assert hdr[-3:] == ["BETA_c1", "BETA_c2", "BETA_c3"] and len(body) == causal.size
