@@ -172,7 +172,7 @@ def run_reference(args, w):
     probe_rows = 64
     rows = np.concatenate([oracle.synth_rows(PANEL_SEED, int(r), 1, n) for r in causal[:probe_rows]])
     t_probe = cpu_port_time(rows, n, k)
-    budget = 150.0
+    budget = 100.0
     per_row = max(t_probe / probe_rows, 1e-7)
     s = int(max(probe_rows, min(w["mc"], budget / ((args.steps + args.warmup) * per_row))))
     # synthesize the sample: the first s causal rows of the same panel the GPU arm uses

@@ -15,6 +15,8 @@
 //
 // This mode is FP64-pipe / shared-memory bound, not HBM bound; it is the
 // parity anchor.  The FAST mode (pheno_lut.cu) is the throughput path.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 namespace {
@@ -23,7 +25,9 @@ constexpr int kChunk = 64;      // SNPs per shared-memory table refill
 constexpr int kThreads = 128;   // byte columns per block (512 samples)
 constexpr int kPrefetch = 8;    // row bytes fetched ahead per thread
 
-template <int K>
+// SPT = samples per thread (1, 2 or 4: a quarter, half or whole packed byte).  Fewer samples
+// per thread means more warps in flight to hide the shared-memory gather -> DADD dependency.
+template <int K, int SPT>
 __global__ void __launch_bounds__(kThreads)
 pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32_t *__restrict__ rows,
                    int64_t mc, int64_t n_samples, const double *__restrict__ freq,
@@ -33,14 +37,14 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
     __shared__ double tbl[kChunk][4][K];      // [snp][raw bits][trait]
     __shared__ int64_t row_off[kChunk];
 
-    const int64_t row_bytes = (n_samples + 3) >> 2;
-    const int64_t col = (int64_t)blockIdx.x * kThreads + threadIdx.x;   // byte column
-    const bool active = col < row_bytes;
-    const uint8_t *base = panel + (active ? col : 0);
+    const int64_t first = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * SPT;   // first sample of this thread
+    const bool active = first < n_samples;
+    const uint8_t *base = panel + (active ? (first >> 2) : 0);
+    const int shift0 = (int)(first & 3) * 2;
 
-    double acc[4][K];
+    double acc[SPT][K];
 #pragma unroll
-    for (int s = 0; s < 4; s++)
+    for (int s = 0; s < SPT; s++)
 #pragma unroll
         for (int k = 0; k < K; k++) acc[s][k] = 0.0;
 
@@ -65,12 +69,12 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
             uint32_t g[kPrefetch];
 #pragma unroll
             for (int u = 0; u < kPrefetch; u++)
-                g[u] = (jj + u < nj) ? (uint32_t)__ldg(base + row_off[jj + u]) : 0u;
+                g[u] = (jj + u < nj) ? ((uint32_t)__ldg(base + row_off[jj + u]) >> shift0) : 0u;
 #pragma unroll
             for (int u = 0; u < kPrefetch; u++) {
                 if (jj + u < nj) {
 #pragma unroll
-                    for (int s = 0; s < 4; s++) {
+                    for (int s = 0; s < SPT; s++) {
                         const uint32_t v = (g[u] >> (2 * s)) & 3u;
 #pragma unroll
                         for (int k = 0; k < K; k++)
@@ -83,8 +87,8 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
 
     if (active) {
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
-            const int64_t i = 4 * col + s;
+        for (int s = 0; s < SPT; s++) {
+            const int64_t i = first + s;
             if (i < n_samples) {
                 y1[i] = acc[s][0];
                 if (K == 2) y2[i] = acc[s][K - 1];
@@ -93,19 +97,37 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
     }
 }
 
+template <int K, int SPT>
+void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq, const double *d_x1,
+                    const double *d_x2, double *d_y1, double *d_y2)
+{
+    const int64_t per_block = (int64_t)kThreads * SPT;
+    const int64_t blocks = (ctx->n_samples + per_block - 1) / per_block;
+    pheno_exact_kernel<K, SPT><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
+        ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
+}
+
 }  // namespace
 
 int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
                        const double *d_x1, const double *d_x2, double *d_y1, double *d_y2)
 {
-    const int64_t blocks = (ctx->row_bytes + kThreads - 1) / kThreads;
+    // measured on B200 (config 2): 4 samples per thread 14.6 ms, 2 -> 16.5 ms, 1 -> slower still:
+    // the kernel is bound by the shared-memory gather (one LDS.64/.128 per update), not by
+    // occupancy, so the widest variant wins.  SIMU_B200_EXACT_SPT overrides for experiments.
+    int spt = 4;
+    if (const char *e = getenv("SIMU_B200_EXACT_SPT")) spt = atoi(e);
+    const bool k2 = d_x2 && d_y2;
     const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
-    if (d_x2 && d_y2)
-        pheno_exact_kernel<2><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
-            ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
-    else
-        pheno_exact_kernel<1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
-            ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, nullptr, d_y1, nullptr);
+    if (k2) {
+        if (spt == 4) launch_exact_t<2, 4>(ctx, d_rows, mc, d_freq, d_x1, d_x2, d_y1, d_y2);
+        else if (spt == 2) launch_exact_t<2, 2>(ctx, d_rows, mc, d_freq, d_x1, d_x2, d_y1, d_y2);
+        else launch_exact_t<2, 1>(ctx, d_rows, mc, d_freq, d_x1, d_x2, d_y1, d_y2);
+    } else {
+        if (spt == 4) launch_exact_t<1, 4>(ctx, d_rows, mc, d_freq, d_x1, nullptr, d_y1, nullptr);
+        else if (spt == 2) launch_exact_t<1, 2>(ctx, d_rows, mc, d_freq, d_x1, nullptr, d_y1, nullptr);
+        else launch_exact_t<1, 1>(ctx, d_rows, mc, d_freq, d_x1, nullptr, d_y1, nullptr);
+    }
     prof_end(ctx, ps);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_exact_kernel launch");
