@@ -348,6 +348,10 @@ def run_ours(args, w):
 
     e2e_step()
     ctx2.sync()
+    t0 = time.perf_counter()                       # staging alone (reported, not part of the timed e2e steps)
+    ctx2.panel_put_rows_ptr(0, mc, host_rows.data_ptr(), B)
+    ctx2.sync()
+    stage_ms = (time.perf_counter() - t0) * 1e3
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -363,6 +367,7 @@ def run_ours(args, w):
     d2h = mc * 24 + 2 * n * 8 * k + 16 * k
     e2e = {"value": updates_step / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "staging_ms": stage_ms, "staging_gbs": mc * B / stage_ms / 1e6,
            "api": "simu_b200_panel_put_rows + find_freq + find_pheno + apply_heritability (host buffers)"}
     # the device-resident and host-buffer paths must agree (same inputs, same kernels)
     e2e_check = float(np.abs(e2e_y[0]).sum() + (np.abs(e2e_y[1]).sum() if k == 2 else 0.0))

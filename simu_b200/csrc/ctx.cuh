@@ -45,6 +45,7 @@ struct simu_b200_ctx {
     int prof_n = 0;
     bool prof_alloc = false;
 
+    bool lut_attr_set[3] = {false, false, false};
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
     std::string err;

@@ -434,10 +434,9 @@ int run_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double 
     double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
     if (!lut || !ypart) return SIMU_B200_ENOMEM;
 
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[K]) {
+    if (!ctx->lut_attr_set[K]) {   // per context: the attribute is per device
         CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        attr_set[K] = true;
+        ctx->lut_attr_set[K] = true;
     }
     CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
     int ps = prof_begin(ctx, PROF_LUT_BUILD);
