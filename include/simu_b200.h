@@ -101,14 +101,19 @@ SIMU_B200_API int simu_b200_panel_free(simu_b200_ctx *ctx);
 
 /* Copy n_rows packed rows from host memory (pitch host_stride >= row_bytes)
  * into panel rows [dst_row, dst_row+n_rows): pinned-host chunked staging on a
- * side stream.  Replaces the fread of bed_read_row (bed.c:343-346). */
+ * side stream (one contiguous DMA per 64 MB chunk + a device re-pitch kernel).
+ * Replaces the fread of bed_read_row (bed.c:343-346).  Pageable sources are
+ * copied through the context's own pinned buffers and may be reused on return;
+ * a PAGE-LOCKED source is read by DMA asynchronously: leave it untouched until
+ * simu_b200_sync() or the next host-buffer hot-path call returns. */
 SIMU_B200_API int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows,
                                            const void *host_rows, int64_t host_stride);
 
 /* Read rows of a .bed file into the panel.  file_rows (ascending row numbers
  * inside this file, NULL = 0..n_rows-1) are the causal rows; all others are
- * seeked past, as pio_skip_row does (bed.c:360-371).  num_loci is the .bim
- * line count.  Validates the 3-byte header (bed_header.c:80-102): returns
+ * seeked past, as pio_skip_row does (bed.c:360-371); runs of adjacent rows are
+ * read with single preads by up to 8 reader threads (SIMU_B200_IO_THREADS).
+ * num_loci is the .bim line count.  Validates the 3-byte header (bed_header.c:80-102): returns
  * SIMU_B200_EFORMAT unless v1.00 SNP-major (source.cc:196-200), SIMU_B200_END
  * if a requested row is >= num_loci (the stream ends early, source.cc:855-858)
  * and SIMU_B200_ERROR on a short read (bed.c:349-352 -> source.cc:226-229). */

@@ -9,7 +9,10 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "ctx.cuh"
 
@@ -414,6 +417,8 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
 
     const int64_t B = ctx->row_bytes;
     const int64_t cap_rows = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / B);
+    int io_threads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char *e = getenv("SIMU_B200_IO_THREADS")) io_threads = std::max(1, atoi(e));
     int buf = 0;
     bool used[2] = {false, false};
     int64_t done = 0, prev = -1;
@@ -424,7 +429,10 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
             if (e != cudaSuccess) { close(fd); return ctx_cuda(ctx, e, "staging event sync"); }
         }
         // coalesce runs of adjacent causal rows into single preads (pio_skip_row defers the
-        // seek the same way, bed.c:333-341)
+        // seek the same way, bed.c:333-341); long runs are cut into <= 4 MB pieces so that the
+        // reader threads stay balanced
+        struct Piece { int64_t file_off, bytes, dst_off; };
+        std::vector<Piece> pieces;
         int64_t q = 0;
         while (q < nr) {
             const int64_t r0 = file_rows ? file_rows[done + q] : done + q;
@@ -437,17 +445,36 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
             }
             int64_t run = 1;
             while (q + run < nr && (file_rows ? file_rows[done + q + run] : r0 + run) == r0 + run) run++;
-            size_t want = (size_t)(run * B), got = 0;
-            while (got < want) {
-                ssize_t k = pread(fd, ctx->pinned[buf] + q * B + got, want - got, (off_t)(3 + r0 * B + (int64_t)got));
-                if (k <= 0) {                           // short read: bed.c:349-352 -> source.cc:226-229
-                    close(fd);
-                    return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Error reading from %s", bed_path);
-                }
-                got += (size_t)k;
-            }
+            const int64_t total = run * B, cut = 4 << 20;
+            for (int64_t o = 0; o < total; o += cut)
+                pieces.push_back({3 + r0 * B + o, std::min(cut, total - o), q * B + o});
             prev = r0 + run - 1;
             q += run;
+        }
+        std::atomic<int> failed{0};
+        uint8_t *dst_base = ctx->pinned[buf];
+        auto reader = [&](int t) {
+            for (size_t i = (size_t)t; i < pieces.size() && !failed.load(std::memory_order_relaxed); i += (size_t)io_threads) {
+                int64_t got = 0;
+                while (got < pieces[i].bytes) {
+                    ssize_t k = pread(fd, dst_base + pieces[i].dst_off + got, (size_t)(pieces[i].bytes - got),
+                                      (off_t)(pieces[i].file_off + got));
+                    if (k <= 0) { failed.store(1); return; }     // short read: bed.c:349-352
+                    got += k;
+                }
+            }
+        };
+        if (io_threads <= 1 || pieces.size() < 2) {
+            reader(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < io_threads; t++) pool.emplace_back(reader, t);
+            reader(0);
+            for (auto &th : pool) th.join();
+        }
+        if (failed.load()) {                            // -> source.cc:226-229
+            close(fd);
+            return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Error reading from %s", bed_path);
         }
         if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + done, buf))) { close(fd); return rc; }
         used[buf] = true;
