@@ -42,7 +42,14 @@ constexpr int kTableBytes = 256 * 128;               // 32 KB
 constexpr int kStageBytes = kBlockRows * kTileBytes + kTableBytes;   // 96 KB
 constexpr int kStages = 2;
 constexpr int kFlushBlocks = 64;
-constexpr int kProducers = 8;                        // TMA-issuing warps
+#ifndef LUT_PRODUCERS
+#define LUT_PRODUCERS 8
+#endif
+#ifndef LUT_UNROLL
+#define LUT_UNROLL 2
+#endif
+constexpr int kProducers = LUT_PRODUCERS;            // TMA-issuing warps
+constexpr int kUnroll = LUT_UNROLL;                  // sub-steps unrolled in the consumer loop
 constexpr int kRowsPerProducer = kBlockRows / kProducers;
 constexpr int kThreads = (kWarps + kProducers) * 32;
 constexpr int kSmemBytes = kStages * kStageBytes + 64 + kProducers * 32 * 8;
@@ -370,7 +377,7 @@ pheno_lut_kernel(const LutParams p)
         const uint32_t table = stage_base + kBlockRows * kTileBytes;
         mbar_wait(full, parity);
 
-#pragma unroll 2
+#pragma unroll kUnroll
         for (int t = 0; t < kGroups; t++) {
             const uint32_t gi = (uint32_t)(lane + t) & 15u;
             const uint32_t wa = words + gi * (4u * kTileBytes);
