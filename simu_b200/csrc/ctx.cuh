@@ -46,6 +46,7 @@ struct simu_b200_ctx {
     bool prof_alloc = false;
 
     bool lut_attr_set[3] = {false, false, false};
+    int coop_sort_blocks = -1;           // co-resident blocks of the cooperative sort (-1: not queried)
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
     std::string err;

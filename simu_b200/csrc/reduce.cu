@@ -9,9 +9,14 @@
 // All three are O(N) / O(N log N) on N <= 500K doubles: latency bound, a few
 // launches each.  They are deterministic (fixed reduction tree, stable LSD
 // radix sort) so repeated runs give identical bits.
+#include <cooperative_groups.h>
 #include <float.h>
 
+#include <algorithm>
+
 #include "ctx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -181,6 +186,124 @@ sort_scatter_kernel(const uint64_t *__restrict__ keys_in, const int32_t *__restr
     }
 }
 
+
+// ---- the same sort as ONE cooperative launch: 8 passes x (histogram | scan | scatter) separated
+// by grid-wide barriers instead of 25 kernel launches.  For N <= 500K the sort is pure launch
+// latency (each kernel runs a few microseconds), so this is what a --cc step actually waits on.
+constexpr int kCoopWarps = 8;
+// kCoopTile = keys per warp-tile (all loaded into registers before they are used): 256 for
+// N <= 200K (more warps, shorter dependent chains), 1024 above (fewer histogram columns to scan)
+
+template <int kCoopTile>
+__global__ void __launch_bounds__(kCoopWarps * 32)
+sort_coop_kernel(const double *__restrict__ y, int64_t n, uint64_t *k0, uint64_t *k1, int32_t *v0, int32_t *v1,
+                 uint32_t *hist, int64_t tiles, int32_t *out_index)
+{
+    constexpr int kCoopPer = kCoopTile / 32;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t cnt[kCoopWarps][256];
+    __shared__ uint32_t digit_base[256];
+    uint32_t *digit_total = hist + tiles * 256;       // 256 extra words behind the histograms
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gwarp = (int64_t)blockIdx.x * kCoopWarps + warp, gwarps = (int64_t)gridDim.x * kCoopWarps;
+
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gthreads) {
+        k0[i] = f64_sort_key(y[i]);
+        v0[i] = (int32_t)i;
+    }
+    grid.sync();
+
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 8 * pass;
+        // ---- per-tile digit histograms
+        for (int64_t tile = gwarp; tile < tiles; tile += gwarps) {
+            for (int d = lane; d < 256; d += 32) cnt[warp][d] = 0;
+            __syncwarp();
+            const int64_t lo = tile * kCoopTile, hi = min(n, lo + kCoopTile);
+            uint64_t kk[kCoopPer];
+#pragma unroll
+            for (int u = 0; u < kCoopPer; u++) { const int64_t i = lo + 32 * u + lane; kk[u] = (i < hi) ? k0[i] : 0; }
+#pragma unroll
+            for (int u = 0; u < kCoopPer; u++)
+                if (lo + 32 * u + lane < hi) atomicAdd(&cnt[warp][(kk[u] >> shift) & 0xFF], 1u);
+            __syncwarp();
+            for (int d = lane; d < 256; d += 32) hist[(int64_t)d * tiles + tile] = cnt[warp][d];
+            __syncwarp();
+        }
+        grid.sync();
+        // ---- exclusive scan over (digit major, tile minor): every warp of the grid scans the tiles
+        // of some digits (coalesced loads + shuffles) and records the digit totals ...
+        for (int64_t d = gwarp; d < 256; d += gwarps) {
+            uint32_t carry = 0;
+            for (int64_t t0 = 0; t0 < tiles; t0 += 32) {
+                const int64_t t = t0 + lane;
+                const uint32_t v = (t < tiles) ? hist[d * tiles + t] : 0u;
+                uint32_t incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                if (t < tiles) hist[d * tiles + t] = carry + incl - v;
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            if (lane == 0) digit_total[d] = carry;
+        }
+        grid.sync();
+        // ... which every block scans for itself (256 values) before scattering
+        if (warp == 0) {
+            uint32_t carry = 0;
+            for (int d0 = 0; d0 < 256; d0 += 32) {
+                const uint32_t v = digit_total[d0 + lane];
+                uint32_t incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                digit_base[d0 + lane] = carry + incl - v;
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+        }
+        __syncthreads();
+        // ---- stable scatter, one warp per tile, 32 keys at a time
+        int32_t *vout = (pass == 7) ? out_index : v1;
+        for (int64_t tile = gwarp; tile < tiles; tile += gwarps) {
+            for (int d = lane; d < 256; d += 32) cnt[warp][d] = hist[(int64_t)d * tiles + tile] + digit_base[d];
+            __syncwarp();
+            const int64_t lo = tile * kCoopTile, hi = min(n, lo + kCoopTile);
+            uint64_t kk[kCoopPer];
+            int32_t vv[kCoopPer];
+#pragma unroll
+            for (int u = 0; u < kCoopPer; u++) {
+                const int64_t i = lo + 32 * u + lane;
+                kk[u] = (i < hi) ? k0[i] : 0;
+                vv[u] = (i < hi) ? v0[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < kCoopPer; u++) {
+                const bool ok = lo + 32 * u + lane < hi;
+                const uint64_t k = kk[u];
+                const int32_t v = vv[u];
+                const uint32_t d = ok ? (uint32_t)((k >> shift) & 0xFF) : 256u + lane;
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                uint32_t dst = 0;
+                if (ok) dst = cnt[warp][d] + rank;
+                __syncwarp();
+                if (ok && rank == 0) cnt[warp][d] += __popc(peers);
+                __syncwarp();
+                if (ok) { k1[dst] = k; vout[dst] = v; }
+            }
+            __syncwarp();
+        }
+        grid.sync();
+        uint64_t *tk = k0; k0 = k1; k1 = tk;
+        int32_t *tv = v0; v0 = v1; v1 = tv;
+    }
+}
+
 }  // namespace
 
 int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out)
@@ -210,12 +333,36 @@ int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32
     if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "argsort: n must be positive");
     const int64_t tiles = (n + kSortTile - 1) / kSortTile;
     const size_t kb = ((size_t)n * 8 + 255) & ~(size_t)255, vb = ((size_t)n * 4 + 255) & ~(size_t)255;
-    const size_t hb = ((size_t)tiles * 256 * 4 + 255) & ~(size_t)255;
+    const size_t hb = (((size_t)(n + 255) / 256 + 1) * 256 * 4 + 255) & ~(size_t)255;   // >= every tile layout
     uint8_t *s = (uint8_t *)ctx_scratch(ctx, SCR_SORT, 2 * kb + 2 * vb + hb);
     if (!s) return SIMU_B200_ENOMEM;
     uint64_t *k0 = (uint64_t *)s, *k1 = (uint64_t *)(s + kb);
     int32_t *v0 = (int32_t *)(s + 2 * kb), *v1 = (int32_t *)(s + 2 * kb + vb);
     uint32_t *hist = (uint32_t *)(s + 2 * kb + 2 * vb);
+    if (ctx->coop_sort_blocks < 0) {      // how many blocks of the cooperative kernel fit on this device
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_coop_kernel<1024>, kCoopWarps * 32, 0) == cudaSuccess)
+            ctx->coop_sort_blocks = per_sm * ctx->num_sms;
+        else
+            ctx->coop_sort_blocks = 0;
+        cudaGetLastError();
+    }
+    if (ctx->coop_sort_blocks > 0) {
+        const int tile = n <= 200000 ? 256 : 1024;
+        int64_t ctiles = (n + tile - 1) / tile;
+        int64_t blocks = (ctiles + kCoopWarps - 1) / kCoopWarps;
+        blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, ctx->coop_sort_blocks));
+        void *args[] = {(void *)&d_key, (void *)&n, (void *)&k0, (void *)&k1, (void *)&v0, (void *)&v1,
+                        (void *)&hist, (void *)&ctiles, (void *)&d_index};
+        const int ps = prof_begin(ctx, PROF_SORT);
+        void *kern = tile == 256 ? (void *)sort_coop_kernel<256> : (void *)sort_coop_kernel<1024>;
+        cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(kCoopWarps * 32), args, 0, ctx->stream);
+        prof_end(ctx, ps);
+        ctx->launches++;
+        return ctx_cuda(ctx, e, "cooperative argsort launch");
+    }
+    // devices without cooperative launch: the same passes as separate kernels
     const unsigned tb = (unsigned)((tiles + kSortWarps - 1) / kSortWarps);
     sort_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_key, n, k0, v0);
     ctx->launches++;
