@@ -241,3 +241,28 @@ def test_trait2_snp_offset(fileset):
     assert close([r[2] for r in body], out[0][0]) and close([r[3] for r in body], out[1][0])
     hdr, body = read_table(d / "off.2.causals")
     assert hdr[-3:] == ["BETA_c1", "BETA_c2", "BETA_c3"] and len(body) == causal.size
+
+
+def test_config1_end_to_end(tmp_path):
+    """BASELINE configs[0] through the drop-in CLI: 10K individuals x 100K SNPs on disk (250 MB .bed),
+    `--qt --causal-n 1000 --hsq 0.5 --seed 1`, against the oracle pipeline on the same files."""
+    import time
+    from simu_b200 import capi
+    n, m = 10_000, 100_000
+    with capi.Context(n) as ctx:                      # write the panel with the device generator
+        ctx.panel_alloc(m)
+        ctx.panel_synth(20240901, 0, m)
+        rows = ctx.panel_get_rows(0, m)
+    plink.write_fileset(str(tmp_path / "syn"), rows, n)
+    t0 = time.perf_counter()
+    out = run(["--bfile", "syn", "--qt", "--causal-n", "1000", "--hsq", "0.5", "--seed", "1", "--out", "c1"], tmp_path, "fast")
+    wall = time.perf_counter() - t0
+    assert "done, 10000 samples, 100000 variants." in out
+    causal, freq, xs, ys = expected_pipeline(rows, n, m, 1, causal_n=1000, hsq=(0.5,))
+    _, body = read_table(tmp_path / "c1.pheno")
+    assert len(body) == n and close([r[2] for r in body], ys[0])
+    _, body = read_table(tmp_path / "c1.1.causals")
+    assert [r[0] for r in body] == [f"rs{v}" for v in causal]
+    assert close([r[5] for r in body], freq) and close([r[6] for r in body], xs[0])
+    print(f"config1 CLI wall time {wall:.2f} s")
+    assert wall < 60
