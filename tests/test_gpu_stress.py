@@ -1,0 +1,60 @@
+"""Shape stress for the FAST (LUT) kernel's work split and pipeline: FAST vs EXACT (the
+bit-exact anchor, itself checked against the oracle elsewhere) over awkward shapes --
+fewer steps than CTAs, one row block, more sample tiles than SMs, row lists with
+repeats and descending order, rows near the end of the panel."""
+import numpy as np
+import pytest
+
+from simu_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n_samples, panel_rows, mc, traits
+    (4096, 70, 1, 1), (4096, 70, 63, 2), (4097, 70, 64, 1), (8191, 200, 65, 2), (8193, 200, 129, 1),
+    (12289, 3000, 2999, 2), (40000, 600, 577, 1), (100003, 300, 300, 2), (250001, 130, 128, 1),
+    (606208, 80, 64, 1),       # 148 sample tiles = one per SM
+    (610305, 70, 70, 2),       # 149 tiles
+    (700001, 40, 33, 1),       # more tiles than CTAs
+    (1000003, 16, 16, 2),
+]
+
+
+@pytest.mark.parametrize("n,m,mc,k", CASES)
+def test_fast_matches_exact(n, m, mc, k):
+    rng = np.random.default_rng(n + 7 * m + mc)
+    sel = rng.integers(0, m, mc).astype(np.int32)            # repeats allowed, unsorted
+    sel[-1] = m - 1
+    x1 = rng.standard_normal(mc) * np.exp(rng.standard_normal(mc))     # wide dynamic range of effects
+    x2 = rng.standard_normal(mc) if k == 2 else None
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m)
+        ctx.panel_synth(99, 0, m)
+        counts, freq = ctx.find_freq(rows=sel)
+        assert np.all(counts.sum(axis=1) == n)
+        e1, e2 = ctx.find_pheno(freq, x1, x2, rows=sel, mode=capi.MODE_EXACT)
+        f1, f2 = ctx.find_pheno(freq, x1, x2, rows=sel, mode=capi.MODE_FAST)
+        g1, g2 = ctx.find_pheno(freq, x1, x2, rows=sel, mode=capi.MODE_FAST)
+    assert np.array_equal(f1, g1)                              # FAST mode is deterministic
+    assert np.max(np.abs(f1 - e1)) <= 1e-5 * np.max(np.abs(e1))
+    if k == 2:
+        assert np.array_equal(f2, g2)
+        assert np.max(np.abs(f2 - e2)) <= 1e-5 * np.max(np.abs(e2))
+
+
+def test_many_contexts_and_reuse():
+    """Contexts are independent; scratch grows and is reused across calls of different sizes."""
+    a, b = capi.Context(1000), capi.Context(5000)
+    try:
+        for ctx, n in ((a, 1000), (b, 5000)):
+            ctx.panel_alloc(300)
+            ctx.panel_synth(5, 0, 300)
+        for mc in (300, 7, 150, 300):
+            for ctx in (a, b):
+                counts, freq = ctx.find_freq(mc=mc)
+                x = np.ones(mc)
+                e, _ = ctx.find_pheno(freq, x, mode=capi.MODE_EXACT)
+                f, _ = ctx.find_pheno(freq, x, mode=capi.MODE_FAST)
+                assert np.max(np.abs(e - f)) <= 1e-5 * max(np.max(np.abs(e)), 1e-300)
+    finally:
+        a.close(); b.close()
