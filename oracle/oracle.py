@@ -33,7 +33,8 @@ def build(force: bool = False) -> None:
     if not need and os.path.getmtime(os.path.join(_HERE, "liboracle.so")) < src_t:
         need = True
     if need or (os.path.isdir("/root/reference/libplinkio/src")
-                and not os.path.exists(os.path.join(_HERE, "_ref", "libsimu_ref.so"))):
+                and not all(os.path.exists(os.path.join(_HERE, "_ref", f))
+                            for f in ("libsimu_ref.so", "libsimu_refsrc.so", "simu_ref"))):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
 
 
@@ -87,6 +88,74 @@ def ref() -> C.CDLL | None:
         R.ref_sample.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_char_p, C.c_int]
         _REF = R
     return _REF
+
+
+_REFSRC = None
+SIMU_REF_BIN = os.path.join(_HERE, "_ref", "simu_ref")
+
+
+def refsrc() -> C.CDLL | None:
+    """The reference's UNMODIFIED src/source.cc compiled against oracle/boost_shim/
+    (oracle/_ref/libsimu_refsrc.so): its literal find_freq / find_pheno / apply_* / main."""
+    global _REFSRC
+    if _REFSRC is None:
+        path = os.path.join(_HERE, "_ref", "libsimu_refsrc.so")
+        if not os.path.exists(path):
+            try:
+                build()
+            except Exception:
+                pass
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_src_last_error.restype = C.c_char_p
+        R.ref_src_freq_pheno.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        R.ref_src_apply_heritability.argtypes = [C.c_float, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
+                                                 C.c_longlong, C.c_void_p]
+        R.ref_src_apply_liability_threshold.argtypes = [C.c_float, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong]
+        _REFSRC = R
+    return _REFSRC
+
+
+def refsrc_freq_pheno(prefix: str, comp, x1, x2=None):
+    """find_freq + find_pheno of the literal reference source on a bfile.
+    -> (freq[M] with NaN for non-causal, pheno1, pheno2 or None, (t_freq, t_pheno) seconds)"""
+    R = refsrc()
+    comp = np.ascontiguousarray(comp, dtype=np.int32)
+    m = comp.size
+    x1 = np.ascontiguousarray(x1, dtype=np.float64)
+    k2 = x2 is not None
+    x2a = np.ascontiguousarray(x2, dtype=np.float64) if k2 else None
+    n = sum(1 for _ in open(prefix + ".fam"))
+    freq = np.zeros(m)
+    p1 = np.zeros(n)
+    p2 = np.zeros(n) if k2 else None
+    secs = np.zeros(2)
+    rc = R.ref_src_freq_pheno(os.fsencode(prefix), 2 if k2 else 1, _ptr(comp), m, _ptr(freq), _ptr(x1), _ptr(x2a),
+                              _ptr(p1), _ptr(p2), _ptr(secs))
+    if rc:
+        raise RuntimeError((R.ref_src_last_error() or b"").decode())
+    return freq, p1, p2, (float(secs[0]), float(secs[1]))
+
+
+def refsrc_apply_heritability(hsq: float, seed: int, pheno, effect):
+    """-> (pheno, effect, noise) after the literal apply_heritability with mt19937(seed)."""
+    R = refsrc()
+    p = np.array(pheno, dtype=np.float64)
+    e = np.array(effect, dtype=np.float64)
+    noise = np.zeros(p.size)
+    if R.ref_src_apply_heritability(hsq, seed, _ptr(p), p.size, _ptr(e), e.size, _ptr(noise)):
+        raise RuntimeError((R.ref_src_last_error() or b"").decode())
+    return p, e, noise
+
+
+def refsrc_apply_liability_threshold(k: float, ncas: int, ncon: int, seed: int, pheno):
+    R = refsrc()
+    p = np.array(pheno, dtype=np.float64)
+    if R.ref_src_apply_liability_threshold(k, ncas, ncon, seed, _ptr(p), p.size):
+        raise RuntimeError((R.ref_src_last_error() or b"").decode())
+    return p
 
 
 def _ptr(a):

@@ -166,8 +166,13 @@ void parse_command_line(int argc, char *argv[], SimuOptions *o)
     int i = 1;
     while (i < argc) {
         std::string tok = argv[i];
-        if (is_number(tok) || tok.size() < 2 || tok[0] != '-')      // source.cc:157-185: a bare value
-            throw OptionError("too many positional options have been specified on the command line");
+        if (is_number(tok) || tok.size() < 2 || tok[0] != '-') {
+            // a bare value that no multitoken option claimed: program_options turns it into a
+            // nameless positional option and, with no positional description given, store()
+            // skips it (source.cc:157-185 makes every number such a positional)
+            i++;
+            continue;
+        }
         std::string name, adjacent;
         bool has_adjacent = false;
         if (tok == "-h") name = "help";

@@ -45,7 +45,7 @@ def run(args, cwd):
     (["--bfile", "x", "--frobnicate"], "Exception  : unrecognised option '--frobnicate'", "err"),
     (["--bfile"], "Exception  : the required argument for option '--bfile' is missing", "err"),
     (["--bfile", "a", "--bfile", "b"], "Exception  : option '--bfile' cannot be specified more than once", "err"),
-    (["stray"], "Exception  : too many positional options have been specified on the command line", "err"),
+    (["stray", "12"], "ERROR: Either --bfile or --bfile-chr must be specified", "out"),   # nameless positionals are skipped
 ])
 def test_validation_messages(tmp_path, args, needle, where):
     rc, out, err = run(args, tmp_path)

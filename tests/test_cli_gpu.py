@@ -266,3 +266,51 @@ def test_config1_end_to_end(tmp_path):
     assert close([r[5] for r in body], freq) and close([r[6] for r in body], xs[0])
     print(f"config1 CLI wall time {wall:.2f} s")
     assert wall < 60
+
+
+# ------------------------------------------------------------------------------------------
+# product CLI against the REFERENCE CLI itself (unmodified source.cc + oracle/boost_shim)
+
+def _run_ref(args, cwd):
+    p = subprocess.run([oracle.SIMU_REF_BIN] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+REF_CASES = [
+    ["--qt", "--causal-n", "50", "--hsq", "0.5", "--seed", "1"],
+    ["--qt", "--num-traits", "2", "--rg", "-0.5", "--gcta-sigma", "--norm-effect", "--causal-pi", "0.1", "--hsq", "0.5", "0.3", "--seed", "7"],
+    ["--cc", "--k", "0.1", "--causal-n", "80", "--seed", "3"],
+    ["--cc", "--num-traits", "2", "--k", "0.2", "0.1", "--ncas", "100", "60", "--ncon", "200", "300", "--causal-n", "40", "--seed", "5"],
+    ["--qt", "--num-components", "2", "--causal-n", "20", "30", "--trait1-sigsq", "1", "0.25", "--trait1-s-pow", "-0.25", "-0.5",
+     "--seed", "9"],
+    ["--qt", "--num-traits", "2", "--causal-n", "40", "--trait2-snp-offset", "1", "--seed", "33"],
+]
+
+
+@pytest.mark.skipif(not os.path.exists(oracle.SIMU_REF_BIN), reason="oracle/_ref/simu_ref absent")
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("case", range(len(REF_CASES)))
+def test_product_cli_equals_reference_cli(fileset, case, mode):
+    d, rows, n, m = fileset
+    args = ["--bfile", "syn"] + REF_CASES[case]
+    ref_log = _run_ref(args + ["--out", f"ref{case}"], d)
+    our_log = run(args + ["--out", f"our{case}_{mode}"], d, mode)
+    k = 2 if "2" == (args[args.index("--num-traits") + 1] if "--num-traits" in args else "1") else 1
+    rh, rb = read_table(d / f"ref{case}.pheno")
+    oh, ob = read_table(d / f"our{case}_{mode}.pheno")
+    assert rh == oh and [r[:2] for r in rb] == [r[:2] for r in ob]
+    for t in range(k):
+        ref_y = np.array([float(r[2 + t]) for r in rb]); our_y = np.array([float(r[2 + t]) for r in ob])
+        if "--cc" in args:
+            assert np.array_equal(ref_y, our_y)                    # labels: exact
+        else:
+            assert close(our_y, ref_y)
+        rh2, rb2 = read_table(d / f"ref{case}.{t+1}.causals")
+        oh2, ob2 = read_table(d / f"our{case}_{mode}.{t+1}.causals")
+        assert rh2 == oh2 and [r[:6] for r in rb2] == [r[:6] for r in ob2]       # SNP CHR POS A1 A2 FRQ: text-identical
+        assert close(np.array([[float(v) for v in r[6:]] for r in ob2]).ravel(),
+                     np.array([[float(v) for v in r[6:]] for r in rb2]).ravel())
+    # the log has the same stage lines (banner version line and timestamps differ)
+    stage = lambda s: [l for l in s.split("\n") if l.endswith("... ") or l.endswith("...") or l.startswith("\t--")]   # noqa: E731
+    assert stage(ref_log) == [l.replace(f"our{case}_{mode}", f"ref{case}") for l in stage(our_log)]
