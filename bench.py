@@ -142,27 +142,48 @@ class ClockSampler:
 
 # ------------------------------------------------------------ reference arm
 
-def cpu_port_time(rows_host, n, k, freq_unused=None, hsq=HSQ):
-    """One pass of the reference algorithm (oracle port) over `rows_host`; -> seconds."""
+def cpu_reference_time(rows_host, n, k, hsq=HSQ):
+    """One pass of the reference's CPU hot path over `rows_host` ([s, ceil(n/4)] packed rows).
+
+    kind "reference": the literal find_freq / find_pheno / apply_heritability of the UNMODIFIED
+    /root/reference/src/source.cc (compiled against oracle/boost_shim into
+    oracle/_ref/libsimu_refsrc.so), reading the rows through the reference's own libplinkio from
+    a temporary bfile, single-threaded as upstream.  Falls back to the line-by-line C port
+    (kind "port") only if that library did not travel.  -> (seconds, kind)"""
+    import tempfile
     from oracle import oracle
     mc = rows_host.shape[0]
     rng = np.random.default_rng(7)
-    t0 = time.perf_counter()
-    _, freq = oracle.find_freq(rows_host, n)
     x1 = rng.standard_normal(mc)
     x2 = rng.standard_normal(mc) if k == 2 else None
+    if oracle.refsrc() is not None:
+        from simu_b200 import plink
+        with tempfile.TemporaryDirectory(prefix="simu_ref_") as d:
+            prefix = os.path.join(d, "sample")
+            plink.write_bed(prefix + ".bed", rows_host, n)
+            plink.write_bim(prefix + ".bim", mc)
+            plink.write_fam(prefix + ".fam", n)
+            comp = np.zeros(mc, dtype=np.int32)
+            _, y1, y2, (t_freq, t_pheno) = oracle.refsrc_freq_pheno(prefix, comp, x1, x2)    # source.cc:843-885, :951-1006
+        t0 = time.perf_counter()
+        oracle.refsrc_apply_heritability(hsq[0], 1, y1, x1)                                   # source.cc:1008-1029
+        if k == 2:
+            oracle.refsrc_apply_heritability(hsq[1], 2, y2, x2)
+        return t_freq + t_pheno + (time.perf_counter() - t0), "reference"
+    t0 = time.perf_counter()
+    _, freq = oracle.find_freq(rows_host, n)
     y1, y2 = oracle.find_pheno(rows_host, n, freq, x1, x2)
     noise = rng.standard_normal(n)
     oracle.apply_heritability(hsq[0], y1, noise, x1)
     if k == 2:
         oracle.apply_heritability(hsq[1], y2, noise, x2)
-    return time.perf_counter() - t0
+    return time.perf_counter() - t0, "port"
 
 
 def run_reference(args, w):
     """The reference's CPU implementation of the path, single-threaded as upstream
-    (/root/reference has no threads: SURVEY.md 0.2).  Source.cc itself needs Boost,
-    which this image lacks, so the line-by-line oracle port is what runs (kind 'port')."""
+    (/root/reference has no threads: SURVEY.md 0.2): the literal functions of the unmodified
+    src/source.cc from oracle/_ref (see cpu_reference_time)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -171,7 +192,7 @@ def run_reference(args, w):
     causal = _causal_rows(w, 0)
     probe_rows = 64
     rows = np.concatenate([oracle.synth_rows(PANEL_SEED, int(r), 1, n) for r in causal[:probe_rows]])
-    t_probe = cpu_port_time(rows, n, k)
+    t_probe, kind = cpu_reference_time(rows, n, k)
     budget = 100.0
     per_row = max(t_probe / probe_rows, 1e-7)
     s = int(max(probe_rows, min(w["mc"], budget / ((args.steps + args.warmup) * per_row))))
@@ -181,11 +202,8 @@ def run_reference(args, w):
     for run in runs:
         rows[run[0]:run[-1] + 1] = oracle.synth_rows(PANEL_SEED, int(causal[run[0]]), run.size, n)
     for _ in range(args.warmup):
-        cpu_port_time(rows, n, k)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_port_time(rows, n, k)
-    dt = (time.perf_counter() - t0) / args.steps
+        cpu_reference_time(rows, n, k)
+    dt = sum(cpu_reference_time(rows, n, k)[0] for _ in range(args.steps)) / args.steps
     value = n * s * k / dt
     sample = f"first {s} of {w['mc']} causal SNP rows x {n} samples per step (same panel, same row list)"
     line = {
@@ -194,8 +212,10 @@ def run_reference(args, w):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "n_samples": n, "n_causal": w["mc"],
                    "traits": k, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": 1, "kind": "port", "sample": sample,
-                         "host_cores": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": "updates/s", "cores": 1, "kind": kind, "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "what": "unmodified src/source.cc find_freq+find_pheno+apply_heritability via its own libplinkio "
+                                 "(oracle/_ref, Boost stand-in headers)" if kind == "reference" else "line-by-line C port"},
         "e2e": {"value": value, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "bed_gbs": s * ((n + 3) // 4) * 2 / dt / 1e9,
@@ -377,10 +397,10 @@ def run_ours(args, w):
     if rank == 0 and world == 1 and not args.no_cpu:
         probe = 64
         rows_np = host_rows.numpy()
-        t_probe = cpu_port_time(rows_np[:probe], n, k)
+        t_probe, _ = cpu_reference_time(rows_np[:probe], n, k)
         s = int(max(probe, min(mc, 15.0 / max(t_probe / probe, 1e-7))))
-        dt = cpu_port_time(rows_np[:s], n, k)
-        cpu = {"value": n * s * k / dt, "unit": "updates/s", "cores": 1, "kind": "port",
+        dt, kind = cpu_reference_time(rows_np[:s], n, k)
+        cpu = {"value": n * s * k / dt, "unit": "updates/s", "cores": 1, "kind": kind,
                "sample": f"first {s} of {mc} causal SNP rows x {n} samples, one pass ({dt:.1f} s)",
                "host_cores": os.cpu_count()}
 

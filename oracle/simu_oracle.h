@@ -9,9 +9,13 @@
  * Parity status: the 2-bit decode and BED header handling are pinned against
  * the reference's own known-answer vectors (libplinkio/tests/bed_test.c) and
  * against the reference's compiled libplinkio (oracle/_ref, see Makefile).
- * find_freq / find_pheno / apply_* have NO golden vectors upstream
- * (the reference ships no tests for src/source.cc): for those functions the
- * oracle is a line-by-line restatement and its parity is "unpinned".
+ * find_freq / find_pheno / apply_* have NO golden vectors upstream (the
+ * reference ships no tests for src/source.cc); they are pinned instead against
+ * the reference ITSELF: the unmodified src/source.cc compiled against
+ * oracle/boost_shim/ into oracle/_ref/libsimu_refsrc.so, whose literal functions
+ * tests/test_reference_source.py compares with this restatement bit for bit.
+ * What stays unpinned is Boost.Random / program_options behaviour, which only a
+ * real Boost build could confirm.
  *
  * Every function cites the reference file:line it follows
  * (paths relative to /root/reference).
