@@ -148,3 +148,42 @@ def test_reference_cli_case_control_and_product_cli_messages(fileset, tmp_path):
         last = lambda s: [l for l in s.strip().split("\n") if l][-1] if s.strip() else ""     # noqa: E731
         assert r1.returncode == r2.returncode == 1
         assert last(r1.stdout + r1.stderr) == last(r2.stdout + r2.stderr), args
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m,k2", [(403, 300, True), (1001, 257, False), (4099, 130, True)])
+def test_cuda_path_equals_reference_source(tmp_path, n, m, k2):
+    """The CUDA path through the C ABI against the LITERAL reference functions on the same bfile:
+    allele frequencies bit-exact, EXACT-mode phenotypes bit-exact, FAST mode within 1e-5,
+    apply_heritability within 1e-12 with the reference's own noise draws."""
+    from simu_b200 import capi
+    rows = oracle.synth_rows(20240901, 11, m, n)
+    rows[3, :] = 0x55
+    prefix = str(tmp_path / "syn")
+    plink.write_fileset(prefix, rows, n)
+    rng = np.random.default_rng(n)
+    comp = np.where(rng.random(m) < 0.5, 0, -1).astype(np.int32)
+    comp[[0, 3, m - 1]] = 0
+    causal = np.flatnonzero(comp != -1)
+    x1, x2 = rng.standard_normal(m), rng.standard_normal(m)
+    freq, p1, p2, _ = oracle.refsrc_freq_pheno(prefix, comp, x1, x2 if k2 else None)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(causal.size)
+        ctx.panel_load_bed(prefix + ".bed", m, causal)
+        _, f = ctx.find_freq()
+        assert np.array_equal(f, freq[causal])
+        e1, e2 = ctx.find_pheno(f, x1[causal], x2[causal] if k2 else None, mode=capi.MODE_EXACT)
+        assert np.array_equal(e1, p1) and (not k2 or np.array_equal(e2, p2))
+        g1, g2 = ctx.find_pheno(f, x1[causal], x2[causal] if k2 else None, mode=capi.MODE_FAST)
+        assert np.max(np.abs(g1 - p1)) <= 1e-5 * np.max(np.abs(p1))
+        if k2:
+            assert np.max(np.abs(g2 - p2)) <= 1e-5 * np.max(np.abs(p2))
+        rp, re, noise = oracle.refsrc_apply_heritability(float(F32(0.6)), 99, p1, x1)
+        gy, gx, _, _ = ctx.apply_heritability(float(F32(0.6)), e1, noise, x1)
+        assert np.max(np.abs(gy - rp)) <= 1e-12 * np.max(np.abs(rp)) and np.max(np.abs(gx - re)) <= 1e-12 * np.max(np.abs(re))
+        lab = oracle.refsrc_apply_liability_threshold(float(F32(0.1)), 10, 50, 5, rp)
+        idx = ctx.liability_order(rp)
+        e = pyrng.Mt19937(5)
+        mc_, mn_ = oracle.liability_split(float(F32(0.1)), n)
+        con = pyrng.random_shuffle(list(range(mn_)), e); cas = pyrng.random_shuffle(list(range(mn_, n)), e)
+        assert np.array_equal(lab, oracle.liability_labels(float(F32(0.1)), 10, 50, idx, con, cas))
