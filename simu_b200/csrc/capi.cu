@@ -350,7 +350,6 @@ int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows
         if ((rc = ensure_pinned(ctx)) || (rc = ensure_dstage(ctx))) return rc;
         const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
         int buf = 0;
-        bool used[2] = {false, false};
         for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1) {
             const int64_t nr = std::min(rows_per, n_rows - r);
             if (ctx->dstage_used[buf]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_copy[buf]));   // DMA out of pinned[buf] done
@@ -361,7 +360,6 @@ int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows
                     memcpy(ctx->pinned[buf] + q * ctx->row_bytes, src + (r + q) * host_stride, (size_t)ctx->row_bytes);
             }
             if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + r, buf))) return rc;
-            used[buf] = true;
         }
         // the caller may free or reuse host_rows on return; pinned[] is ours, nothing to wait for
         return SIMU_B200_OK;
@@ -420,7 +418,6 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
     int io_threads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     if (const char *e = getenv("SIMU_B200_IO_THREADS")) io_threads = std::max(1, atoi(e));
     int buf = 0;
-    bool used[2] = {false, false};
     int64_t done = 0, prev = -1;
     while (done < n_rows) {
         const int64_t nr = std::min(cap_rows, n_rows - done);
@@ -477,7 +474,6 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
             return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Error reading from %s", bed_path);
         }
         if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + done, buf))) { close(fd); return rc; }
-        used[buf] = true;
         buf ^= 1;
         done += nr;
     }

@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(1024)
 sort_scan_kernel(uint32_t *__restrict__ hist, int64_t len)
 {
     __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t per = (len + 1023) / 1024;
     const int64_t lo = min(len, per * threadIdx.x), hi = min(len, lo + per);
@@ -140,7 +139,6 @@ sort_scan_kernel(uint32_t *__restrict__ hist, int64_t len)
         if (lane >= o) incl += t;
     }
     if (lane == 31) warp_sum[warp] = incl;
-    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
     if (warp == 0) {
         uint32_t w = warp_sum[lane], wi = w;
