@@ -37,7 +37,7 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
     __shared__ double tbl[kChunk][4][K];      // [snp][raw bits][trait]
     __shared__ int64_t row_off[kChunk];
 
-    const int64_t first = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * SPT;   // first sample of this thread
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * SPT;   // first sample of this thread
     const bool active = first < n_samples;
     const uint8_t *base = panel + (active ? (first >> 2) : 0);
     const int shift0 = (int)(first & 3) * 2;
@@ -51,17 +51,17 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
     for (int64_t j0 = 0; j0 < mc; j0 += kChunk) {
         const int nj = (int)min((int64_t)kChunk, mc - j0);
         __syncthreads();
-        if (threadIdx.x < nj) {
-            const int64_t j = j0 + threadIdx.x;
+        for (int t = threadIdx.x; t < nj; t += blockDim.x) {
+            const int64_t j = j0 + t;
             const double avg = __dmul_rn(2.0, freq[j]);          // source.cc:986
-            row_off[threadIdx.x] = (rows ? (int64_t)rows[j] : j) * row_stride;
+            row_off[t] = (rows ? (int64_t)rows[j] : j) * row_stride;
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const double x = (k == 0) ? x1[j] : x2[j];
-                tbl[threadIdx.x][0][k] = __dmul_rn(__dsub_rn(2.0, avg), x);   // bits 00: two A1 copies
-                tbl[threadIdx.x][1][k] = 0.0;                                 // bits 01: missing (:991)
-                tbl[threadIdx.x][2][k] = __dmul_rn(__dsub_rn(1.0, avg), x);   // bits 10: one copy
-                tbl[threadIdx.x][3][k] = __dmul_rn(__dsub_rn(0.0, avg), x);   // bits 11: none
+                tbl[t][0][k] = __dmul_rn(__dsub_rn(2.0, avg), x);   // bits 00: two A1 copies
+                tbl[t][1][k] = 0.0;                                 // bits 01: missing (:991)
+                tbl[t][2][k] = __dmul_rn(__dsub_rn(1.0, avg), x);   // bits 10: one copy
+                tbl[t][3][k] = __dmul_rn(__dsub_rn(0.0, avg), x);   // bits 11: none
             }
         }
         __syncthreads();
@@ -101,9 +101,13 @@ template <int K, int SPT>
 void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq, const double *d_x1,
                     const double *d_x2, double *d_y1, double *d_y2)
 {
-    const int64_t per_block = (int64_t)kThreads * SPT;
+    // small blocks: the block count should be several times the SM count, or the last wave is
+    // half empty (N = 100K with 128-thread blocks gives 196 blocks on 148 SMs: 2x the time)
+    int threads = 128;
+    if (const char *e = getenv("SIMU_B200_EXACT_THREADS")) threads = atoi(e);
+    const int64_t per_block = (int64_t)threads * SPT;
     const int64_t blocks = (ctx->n_samples + per_block - 1) / per_block;
-    pheno_exact_kernel<K, SPT><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(
+    pheno_exact_kernel<K, SPT><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
         ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
 }
 
@@ -112,10 +116,11 @@ void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const
 int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
                        const double *d_x1, const double *d_x2, double *d_y1, double *d_y2)
 {
-    // measured on B200 (config 2): 4 samples per thread 14.6 ms, 2 -> 16.5 ms, 1 -> slower still:
-    // the kernel is bound by the shared-memory gather (one LDS.64/.128 per update), not by
-    // occupancy, so the widest variant wins.  SIMU_B200_EXACT_SPT overrides for experiments.
-    int spt = 4;
+    // measured on B200 (config 2, K=2): 13.6-17 ms for every combination of 1/2/4 samples per
+    // thread and 32/64/128 threads per block -- the kernel is bound by its per-update
+    // shared-memory gather + FP64 add chain, not by occupancy.  SIMU_B200_EXACT_SPT /
+    // SIMU_B200_EXACT_THREADS override for experiments.
+    int spt = 2;
     if (const char *e = getenv("SIMU_B200_EXACT_SPT")) spt = atoi(e);
     const bool k2 = d_x2 && d_y2;
     const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
