@@ -56,7 +56,9 @@ enum simu_b200_mode {
      * subtract/multiply/add: bit-identical to source.cc:986-996 on one GPU. */
     SIMU_B200_MODE_EXACT = 0,
     /* 4-SNP lookup tables in FP32 (entries rounded from FP64), FP32 partial
-     * sums flushed to FP64: |dy| <= 1e-5 * max|y| (tests state the bound). */
+     * sums flushed to FP64: |dy| <= 1e-5 * max|y| (tests state the bound).
+     * Table entries and 1024-term partial sums must fit FP32: use EXACT mode
+     * for effect sizes beyond ~1e33 in magnitude. */
     SIMU_B200_MODE_FAST = 1
 };
 
