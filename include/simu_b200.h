@@ -62,6 +62,20 @@ enum simu_b200_mode {
     SIMU_B200_MODE_FAST = 1
 };
 
+/* How the panel is laid out in HBM. */
+enum simu_b200_layout {
+    /* One SNP row after the other, exactly as in the .bed, at a 128-byte pitch.  Any row of a
+     * resident panel can be addressed through the `rows` lists of find_freq / find_pheno
+     * (several simulations with different causal sets over one resident panel). */
+    SIMU_B200_LAYOUT_ROWS = 0,
+    /* Four consecutive rows stored sample-interleaved: byte i of group g holds the 2-bit fields of
+     * sample i for rows 4g..4g+3 (row 4g in bits 0-1).  For COMPACT panels -- only the causal rows
+     * staged, in causal order, which is what the reference reads (source.cc:852-863) -- so `rows`
+     * must be NULL.  find_pheno's FAST kernel then needs no bit transposition (config 4: 8.3 ->
+     * 6.7 ms); the interleave rides on the staging pass, which rewrites every row anyway. */
+    SIMU_B200_LAYOUT_GROUP4 = 1
+};
+
 typedef struct simu_b200_ctx simu_b200_ctx;
 
 /* ------------------------------------------------------------------ context */
@@ -98,12 +112,18 @@ SIMU_B200_API int64_t simu_b200_row_stride(const simu_b200_ctx *ctx);
 SIMU_B200_API int64_t simu_b200_panel_rows(const simu_b200_ctx *ctx);
 SIMU_B200_API void *simu_b200_panel_device_ptr(const simu_b200_ctx *ctx);
 
+/* panel_alloc = panel_alloc_layout(SIMU_B200_LAYOUT_ROWS).  The panel is zero-filled (all 00). */
 SIMU_B200_API int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows);
+SIMU_B200_API int simu_b200_panel_alloc_layout(simu_b200_ctx *ctx, int64_t num_rows, int layout);
+SIMU_B200_API int simu_b200_panel_layout(const simu_b200_ctx *ctx);
+/* GROUP4: bytes between consecutive 4-row groups = round_up(N, 128). */
+SIMU_B200_API int64_t simu_b200_group_stride(const simu_b200_ctx *ctx);
 SIMU_B200_API int simu_b200_panel_free(simu_b200_ctx *ctx);
 
 /* Copy n_rows packed rows from host memory (pitch host_stride >= row_bytes)
  * into panel rows [dst_row, dst_row+n_rows): pinned-host chunked staging on a
- * side stream (one contiguous DMA per 64 MB chunk + a device re-pitch kernel).
+ * side stream (one contiguous DMA per 64 MB chunk + a device re-pitch / interleave
+ * kernel).  Rows may be appended at any offset, also inside a GROUP4 group.
  * Replaces the fread of bed_read_row (bed.c:343-346).  Pageable sources are
  * copied through the context's own pinned buffers and may be reused on return;
  * a PAGE-LOCKED source is read by DMA asynchronously: leave it untouched until
@@ -128,7 +148,13 @@ SIMU_B200_API int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_p
 SIMU_B200_API int simu_b200_panel_synth(simu_b200_ctx *ctx, uint64_t panel_seed, int64_t first_row,
                                         int64_t n_rows, int64_t dst_row);
 
-/* Copy panel rows back to the host (tests, e2e staging of synthetic data). */
+/* Same generator for a scattered list of global SNP rows (HOST array row_ids, e.g. the causal
+ * rows of a sparse configuration) -> panel rows dst_row + r. */
+SIMU_B200_API int simu_b200_panel_synth_rows(simu_b200_ctx *ctx, uint64_t panel_seed, const int64_t *row_ids,
+                                             int64_t n_rows, int64_t dst_row);
+
+/* Copy panel rows back to the host as packed .bed rows, whatever the layout (tests, e2e
+ * staging of synthetic data). */
 SIMU_B200_API int simu_b200_panel_get_rows(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows,
                                            void *host_rows, int64_t host_stride);
 
@@ -137,7 +163,8 @@ SIMU_B200_API int simu_b200_panel_get_rows(simu_b200_ctx *ctx, int64_t src_row, 
  * functions today; all pointers are HOST pointers. */
 
 /* find_freq (source.cc:843-885) over the causal SNPs.  rows[j] = panel row of
- * the j-th causal SNP in ascending variant order (NULL = 0..mc-1).
+ * the j-th causal SNP in ascending variant order (NULL = 0..mc-1; must be NULL
+ * for a GROUP4 panel).
  * counts: mc x 4 = genocount[0..3] (source.cc:869), freq: mc doubles with the
  * exact expression of source.cc:874-875.  Either may be NULL. */
 SIMU_B200_API int simu_b200_find_freq(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc,

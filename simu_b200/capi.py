@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("SIMU_B200_LIB") or os.path.join(_PKG, "lib", "libsimu
 
 OK, END, ERROR, EINVAL, ECUDA, ENOMEM, EFORMAT = range(7)
 MODE_EXACT, MODE_FAST = 0, 1
+LAYOUT_ROWS, LAYOUT_GROUP4 = 0, 1
 
 # every symbol include/simu_b200.h declares: (name, restype, argtypes)
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
@@ -35,6 +36,10 @@ SIGNATURES = {
     "simu_b200_panel_rows": (_i64, [_vp]),
     "simu_b200_panel_device_ptr": (_vp, [_vp]),
     "simu_b200_panel_alloc": (_i32, [_vp, _i64]),
+    "simu_b200_panel_alloc_layout": (_i32, [_vp, _i64, _i32]),
+    "simu_b200_panel_layout": (_i32, [_vp]),
+    "simu_b200_group_stride": (_i64, [_vp]),
+    "simu_b200_panel_synth_rows": (_i32, [_vp, C.c_uint64, _vp, _i64, _i64]),
     "simu_b200_panel_free": (_i32, [_vp]),
     "simu_b200_panel_put_rows": (_i32, [_vp, _i64, _i64, _vp, _i64]),
     "simu_b200_panel_load_bed": (_i32, [_vp, C.c_char_p, _i64, _vp, _i64, _i64]),
@@ -155,8 +160,17 @@ class Context:
     def panel_ptr(self) -> int:
         return int(self.lib.simu_b200_panel_device_ptr(self.h) or 0)
 
-    def panel_alloc(self, rows: int):
-        self._check(self.lib.simu_b200_panel_alloc(self.h, rows))
+    def panel_alloc(self, rows: int, layout: int = LAYOUT_ROWS):
+        """layout: LAYOUT_ROWS (row lists allowed) or LAYOUT_GROUP4 (compact causal panel, rows=None)."""
+        self._check(self.lib.simu_b200_panel_alloc_layout(self.h, rows, layout))
+
+    @property
+    def layout(self) -> int:
+        return int(self.lib.simu_b200_panel_layout(self.h))
+
+    @property
+    def group_stride(self) -> int:
+        return int(self.lib.simu_b200_group_stride(self.h))
 
     def panel_free(self):
         self._check(self.lib.simu_b200_panel_free(self.h))
@@ -186,6 +200,10 @@ class Context:
 
     def panel_synth(self, seed: int, first_row: int, n_rows: int, dst_row: int = 0):
         self._check(self.lib.simu_b200_panel_synth(self.h, seed, first_row, n_rows, dst_row))
+
+    def panel_synth_rows(self, seed: int, row_ids, dst_row: int = 0):
+        ids = np.ascontiguousarray(row_ids, dtype=np.int64)
+        self._check(self.lib.simu_b200_panel_synth_rows(self.h, seed, _np_ptr(ids), ids.size, dst_row))
 
     # -- hot path, host buffers ----------------------------------------------
     def find_freq(self, rows=None, mc: int | None = None):

@@ -91,6 +91,8 @@ const char *simu_b200_last_error(const simu_b200_ctx *ctx) { return ctx ? ctx->e
 
 int64_t simu_b200_row_bytes(int64_t num_samples) { return (num_samples + 3) / 4; }   // bed_header.c:219-223
 int64_t simu_b200_row_stride(const simu_b200_ctx *ctx) { return ctx ? ctx->row_stride : 0; }
+int64_t simu_b200_group_stride(const simu_b200_ctx *ctx) { return ctx ? ctx->group_stride : 0; }
+int simu_b200_panel_layout(const simu_b200_ctx *ctx) { return ctx ? ctx->layout : SIMU_B200_LAYOUT_ROWS; }
 int64_t simu_b200_panel_rows(const simu_b200_ctx *ctx) { return ctx ? ctx->panel_rows : 0; }
 void *simu_b200_panel_device_ptr(const simu_b200_ctx *ctx) { return ctx ? ctx->panel : nullptr; }
 int64_t simu_b200_launch_count(const simu_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
@@ -122,6 +124,7 @@ int simu_b200_open(simu_b200_ctx **out, int device, int64_t num_samples)
     ctx->n_samples = num_samples;
     ctx->row_bytes = simu_b200_row_bytes(num_samples);
     ctx->row_stride = (ctx->row_bytes + SIMU_ROW_ALIGN - 1) / SIMU_ROW_ALIGN * SIMU_ROW_ALIGN;
+    ctx->group_stride = (num_samples + SIMU_ROW_ALIGN - 1) / SIMU_ROW_ALIGN * SIMU_ROW_ALIGN;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess ||
@@ -225,22 +228,32 @@ int simu_b200_panel_free(simu_b200_ctx *ctx)
     return SIMU_B200_OK;
 }
 
-int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows)
+int simu_b200_panel_alloc_layout(simu_b200_ctx *ctx, int64_t num_rows, int layout)
 {
     if (!ctx) return SIMU_B200_EINVAL;
     if (num_rows <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_alloc: num_rows must be positive");
+    if (layout != SIMU_B200_LAYOUT_ROWS && layout != SIMU_B200_LAYOUT_GROUP4)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_alloc: unknown layout %d", layout);
     int rc = simu_b200_panel_free(ctx);
     if (rc) return rc;
-    const size_t bytes = (size_t)num_rows * (size_t)ctx->row_stride;
+    const size_t bytes = layout == SIMU_B200_LAYOUT_GROUP4 ? (size_t)((num_rows + 3) / 4) * (size_t)ctx->group_stride
+                                                           : (size_t)num_rows * (size_t)ctx->row_stride;
     cudaError_t e = cudaMalloc((void **)&ctx->panel, bytes);
     if (e != cudaSuccess)
         return ctx_fail(ctx, SIMU_B200_ENOMEM, "panel_alloc: cannot allocate %zu bytes of HBM (%s)", bytes,
                         cudaGetErrorString(e));
     ctx->panel_rows = num_rows;
+    ctx->layout = layout;
     // pitch padding is never interpreted by the kernels (they mask to N); zero it once so that
-    // panel_get_rows and debuggers see defined bytes.
+    // panel_get_rows and debuggers see defined bytes.  GROUP4: rows of a group that have not been
+    // written yet read as 00 until they are.
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->panel, 0, bytes, ctx->stream));
     return SIMU_B200_OK;
+}
+
+int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows)
+{
+    return simu_b200_panel_alloc_layout(ctx, num_rows, SIMU_B200_LAYOUT_ROWS);
 }
 
 static int ensure_pinned(simu_b200_ctx *ctx)
@@ -269,16 +282,22 @@ static int ensure_dstage(simu_b200_ctx *ctx)
     return SIMU_B200_OK;
 }
 
-// One chunk of contiguous packed rows (page-locked host memory) -> panel rows:
-// 1-D DMA on the copy stream into bounce buffer `buf`, re-pitch kernel on the compute stream.
-static int stage_chunk(simu_b200_ctx *ctx, const uint8_t *pinned_src, int64_t nr, int64_t dst_row, int buf)
+// One chunk of packed rows in page-locked host memory (pitch src_stride) -> panel rows: DMA on the
+// copy stream into bounce buffer `buf` (rows contiguous there: one 1-D copy when the source is
+// contiguous too), then the re-pitch / interleave kernel on the compute stream.
+static int stage_chunk(simu_b200_ctx *ctx, const uint8_t *pinned_src, int64_t src_stride, int64_t nr, int64_t dst_row,
+                       int buf)
 {
     if (ctx->dstage_used[buf]) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_repitch[buf], 0));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dstage[buf], pinned_src, (size_t)(nr * ctx->row_bytes), cudaMemcpyHostToDevice,
-                                  ctx->copy_stream));
+    if (src_stride == ctx->row_bytes)
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->dstage[buf], pinned_src, (size_t)(nr * ctx->row_bytes), cudaMemcpyHostToDevice,
+                                      ctx->copy_stream));
+    else
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->dstage[buf], (size_t)ctx->row_bytes, pinned_src, (size_t)src_stride,
+                                        (size_t)ctx->row_bytes, (size_t)nr, cudaMemcpyHostToDevice, ctx->copy_stream));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_copy[buf], ctx->copy_stream));
     CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[buf], 0));
-    int rc = launch_repitch(ctx, ctx->dstage[buf], nr, dst_row, ctx->stream);
+    int rc = launch_repitch(ctx, ctx->dstage[buf], ctx->row_bytes, nr, dst_row, ctx->stream);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_repitch[buf], ctx->stream));
     ctx->dstage_used[buf] = true;
@@ -327,44 +346,32 @@ int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows
     bool is_pinned = (cudaPointerGetAttributes(&attr, host_rows) == cudaSuccess) && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     const uint8_t *src = (const uint8_t *)host_rows;
-    if (is_pinned && host_stride == ctx->row_bytes) {
-        // page-locked and contiguous: chunked 1-D DMA straight from the caller's buffer into the
-        // device bounce buffers, re-pitched on the compute stream while the next chunk copies
-        if ((rc = ensure_dstage(ctx))) return rc;
-        const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
-        int buf = 0;
-        for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1)
-            if ((rc = stage_chunk(ctx, src + r * host_stride, std::min(rows_per, n_rows - r), dst_row + r, buf))) return rc;
-        return SIMU_B200_OK;      // the compute stream is already ordered behind the last re-pitch
-    }
+    if ((rc = ensure_dstage(ctx))) return rc;
+    // rows_per is a multiple of 4 so that GROUP4 chunk boundaries fall on group boundaries
+    const int64_t rows_per = std::max<int64_t>(4, ((int64_t)SIMU_STAGE_BYTES / ctx->row_bytes) & ~(int64_t)3);
+    int buf = 0;
     if (is_pinned) {
-        // page-locked but strided: pitched 2-D DMA from the caller's buffer
-        const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
-        for (int64_t r = 0; r < n_rows; r += rows_per) {
-            const int64_t nr = std::min(rows_per, n_rows - r);
-            CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->panel + (dst_row + r) * ctx->row_stride, (size_t)ctx->row_stride,
-                                            src + r * host_stride, (size_t)host_stride, (size_t)ctx->row_bytes,
-                                            (size_t)nr, cudaMemcpyHostToDevice, ctx->copy_stream));
-        }
-    } else {
-        if ((rc = ensure_pinned(ctx)) || (rc = ensure_dstage(ctx))) return rc;
-        const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
-        int buf = 0;
-        for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1) {
-            const int64_t nr = std::min(rows_per, n_rows - r);
-            if (ctx->dstage_used[buf]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_copy[buf]));   // DMA out of pinned[buf] done
-            if (host_stride == ctx->row_bytes) {
-                memcpy(ctx->pinned[buf], src + r * host_stride, (size_t)(nr * ctx->row_bytes));
-            } else {
-                for (int64_t q = 0; q < nr; q++)
-                    memcpy(ctx->pinned[buf] + q * ctx->row_bytes, src + (r + q) * host_stride, (size_t)ctx->row_bytes);
-            }
-            if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + r, buf))) return rc;
-        }
-        // the caller may free or reuse host_rows on return; pinned[] is ours, nothing to wait for
-        return SIMU_B200_OK;
+        // page-locked: chunked DMA straight from the caller's buffer into the device bounce
+        // buffers, re-pitched / interleaved on the compute stream while the next chunk copies
+        for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1)
+            if ((rc = stage_chunk(ctx, src + r * host_stride, host_stride, std::min(rows_per, n_rows - r), dst_row + r, buf)))
+                return rc;
+        return SIMU_B200_OK;      // the compute stream is already ordered behind the last kernel
     }
-    return join_copy_stream(ctx);
+    if ((rc = ensure_pinned(ctx))) return rc;
+    for (int64_t r = 0; r < n_rows; r += rows_per, buf ^= 1) {
+        const int64_t nr = std::min(rows_per, n_rows - r);
+        if (ctx->dstage_used[buf]) CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_copy[buf]));   // DMA out of pinned[buf] done
+        if (host_stride == ctx->row_bytes) {
+            memcpy(ctx->pinned[buf], src + r * host_stride, (size_t)(nr * ctx->row_bytes));
+        } else {
+            for (int64_t q = 0; q < nr; q++)
+                memcpy(ctx->pinned[buf] + q * ctx->row_bytes, src + (r + q) * host_stride, (size_t)ctx->row_bytes);
+        }
+        if ((rc = stage_chunk(ctx, ctx->pinned[buf], ctx->row_bytes, nr, dst_row + r, buf))) return rc;
+    }
+    // the caller may free or reuse host_rows on return; pinned[] is ours, nothing to wait for
+    return SIMU_B200_OK;
 }
 
 int simu_b200_panel_get_rows(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows, void *host_rows,
@@ -377,15 +384,18 @@ int simu_b200_panel_get_rows(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows
     if (n_rows == 0) return SIMU_B200_OK;
     if (!host_rows || host_stride < ctx->row_bytes)
         return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_get_rows: bad host buffer");
-    // chunk so that a single 2D copy never exceeds the pitch/height limits
-    const int64_t rows_per = std::max<int64_t>(1, (int64_t)(256u << 20) / ctx->row_bytes);
+    if ((rc = ensure_dstage(ctx))) return rc;
+    // gather the rows into a bounce buffer (contiguous, pitch row_bytes) and copy that out
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    const int64_t rows_per = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / ctx->row_bytes);
     for (int64_t r = 0; r < n_rows; r += rows_per) {
         const int64_t nr = std::min(rows_per, n_rows - r);
-        CUDA_TRY(ctx, cudaMemcpy2DAsync((uint8_t *)host_rows + r * host_stride, (size_t)host_stride,
-                                        ctx->panel + (src_row + r) * ctx->row_stride, (size_t)ctx->row_stride,
-                                        (size_t)ctx->row_bytes, (size_t)nr, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = launch_unpanel(ctx, src_row + r, nr, ctx->dstage[0], ctx->stream))) return rc;
+        CUDA_TRY(ctx, cudaMemcpy2DAsync((uint8_t *)host_rows + r * host_stride, (size_t)host_stride, ctx->dstage[0],
+                                        (size_t)ctx->row_bytes, (size_t)ctx->row_bytes, (size_t)nr,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return SIMU_B200_OK;
 }
 
@@ -414,7 +424,7 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
     if ((rc = ensure_pinned(ctx)) || (rc = ensure_dstage(ctx)) || (rc = fork_copy_stream(ctx))) { close(fd); return rc; }
 
     const int64_t B = ctx->row_bytes;
-    const int64_t cap_rows = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / B);
+    const int64_t cap_rows = std::max<int64_t>(4, ((int64_t)SIMU_STAGE_BYTES / B) & ~(int64_t)3);
     int io_threads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     if (const char *e = getenv("SIMU_B200_IO_THREADS")) io_threads = std::max(1, atoi(e));
     int buf = 0;
@@ -473,13 +483,42 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
             close(fd);
             return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Error reading from %s", bed_path);
         }
-        if ((rc = stage_chunk(ctx, ctx->pinned[buf], nr, dst_row + done, buf))) { close(fd); return rc; }
+        if ((rc = stage_chunk(ctx, ctx->pinned[buf], B, nr, dst_row + done, buf))) { close(fd); return rc; }
         buf ^= 1;
         done += nr;
     }
     close(fd);
     // the pinned buffers are reused by the next call: drain the DMA queue before returning
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return SIMU_B200_OK;
+}
+
+// rows first_row + r, or row_ids[r] (host list), r < n_rows -> panel rows dst_row + r
+static int synth_into_panel(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, const int64_t *row_ids, int64_t n_rows,
+                            int64_t dst_row)
+{
+    int64_t *d_ids = nullptr;
+    if (row_ids) {
+        d_ids = (int64_t *)ctx_scratch(ctx, SCR_MISC, (size_t)n_rows * 8);
+        if (!d_ids) return SIMU_B200_ENOMEM;
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_ids, row_ids, (size_t)n_rows * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // row_ids may be pageable
+    }
+    if (ctx->layout == SIMU_B200_LAYOUT_ROWS)
+        return launch_synth(ctx, seed, first_row, d_ids, n_rows, ctx->panel + dst_row * ctx->row_stride, ctx->row_stride);
+    // GROUP4: generate packed rows chunk by chunk into a bounce buffer, then interleave
+    int rc = ensure_dstage(ctx);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    const int64_t pitch = ctx->row_stride;
+    const int64_t rows_per = std::max<int64_t>(4, ((int64_t)SIMU_STAGE_BYTES / pitch) & ~(int64_t)3);
+    int64_t r = 0;
+    while (r < n_rows) {
+        const int64_t nr = std::min(rows_per, n_rows - r);
+        if ((rc = launch_synth(ctx, seed, first_row + r, d_ids ? d_ids + r : nullptr, nr, ctx->dstage[0], pitch))) return rc;
+        if ((rc = launch_repitch(ctx, ctx->dstage[0], pitch, nr, dst_row + r, ctx->stream))) return rc;
+        r += nr;
+    }
     return SIMU_B200_OK;
 }
 
@@ -490,16 +529,30 @@ int simu_b200_panel_synth(simu_b200_ctx *ctx, uint64_t panel_seed, int64_t first
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = check_rows(ctx, "panel_synth", dst_row, n_rows);
     if (rc) return rc;
-    return launch_synth(ctx, panel_seed, first_row, n_rows, dst_row);
+    return synth_into_panel(ctx, panel_seed, first_row, nullptr, n_rows, dst_row);
+}
+
+int simu_b200_panel_synth_rows(simu_b200_ctx *ctx, uint64_t panel_seed, const int64_t *row_ids, int64_t n_rows,
+                               int64_t dst_row)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = check_rows(ctx, "panel_synth_rows", dst_row, n_rows);
+    if (rc) return rc;
+    if (n_rows > 0 && !row_ids) return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_synth_rows: row_ids is NULL");
+    return synth_into_panel(ctx, panel_seed, 0, row_ids, n_rows, dst_row);
 }
 
 // ------------------------------------------------ device-resident variants
 
-static int check_hot(simu_b200_ctx *ctx, const char *who, int64_t mc)
+static int check_hot(simu_b200_ctx *ctx, const char *who, int64_t mc, const void *rows)
 {
     if (!ctx) return SIMU_B200_EINVAL;
     if (!ctx->panel) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: no panel allocated", who);
     if (mc < 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: negative causal count", who);
+    if (rows && ctx->layout == SIMU_B200_LAYOUT_GROUP4)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: a GROUP4 panel is compact (stage the causal rows only, in causal "
+                        "order); row lists need a ROWS panel", who);
     cudaError_t e = cudaSetDevice(ctx->device);
     return ctx_cuda(ctx, e, "cudaSetDevice");
 }
@@ -507,7 +560,7 @@ static int check_hot(simu_b200_ctx *ctx, const char *who, int64_t mc)
 int simu_b200_find_freq_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts,
                             double *d_freq)
 {
-    int rc = check_hot(ctx, "find_freq", mc);
+    int rc = check_hot(ctx, "find_freq", mc, d_rows);
     if (rc) return rc;
     if (!d_rows && mc > ctx->panel_rows)
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq: %lld causal rows but panel holds %lld", (long long)mc,
@@ -519,7 +572,7 @@ int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t 
                              const double *d_effect1, const double *d_effect2, double *d_pheno1,
                              double *d_pheno2, int mode)
 {
-    int rc = check_hot(ctx, "find_pheno", mc);
+    int rc = check_hot(ctx, "find_pheno", mc, d_rows);
     if (rc) return rc;
     if (!d_rows && mc > ctx->panel_rows)
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: %lld causal rows but panel holds %lld", (long long)mc,
@@ -583,7 +636,7 @@ static int check_row_list(simu_b200_ctx *ctx, const char *who, const int32_t *ro
 
 int simu_b200_find_freq(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, int32_t *counts, double *freq)
 {
-    int rc = check_hot(ctx, "find_freq", mc);
+    int rc = check_hot(ctx, "find_freq", mc, rows);
     if (rc || (rc = check_row_list(ctx, "find_freq", rows, mc))) return rc;
     if (mc == 0) return SIMU_B200_OK;
     void *d_rows = nullptr;
@@ -604,7 +657,7 @@ int simu_b200_find_freq(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, int
 int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, const double *freq,
                          const double *effect1, const double *effect2, double *pheno1, double *pheno2, int mode)
 {
-    int rc = check_hot(ctx, "find_pheno", mc);
+    int rc = check_hot(ctx, "find_pheno", mc, rows);
     if (rc || (rc = check_row_list(ctx, "find_pheno", rows, mc))) return rc;
     if (!pheno1 || ((effect2 == nullptr) != (pheno2 == nullptr)) || (mc > 0 && (!freq || !effect1)))
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: NULL argument (effect2/pheno2 must be both set or both NULL)");

@@ -111,18 +111,163 @@ counts_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32
     }
 }
 
+// ------------------------------------------------------------ GROUP4 layout
+//
+// In a GROUP4 panel a 32-bit word holds 4 samples x 4 SNP rows (row r of the group in bits
+// 8s+2r, 8s+2r+1), so ONE pass over a group yields the counts of its four SNPs: the words go
+// through the same carry-save tree, only the final POPCs are taken under per-row masks.  The
+// tree is one level deeper than above (ones/twos/fours/eights, POPC of the weight-16 word:
+// 12 POPC per 256 genotypes) because there are 12 masked POPCs per tree output instead of 2.
+// The lo&hi plane is fed into a second tree as w & (w >> 1): its odd bits are garbage, but
+// carry-save adders are bitwise, so they never reach the even bits the masks select.
+// SPLIT warps of a CTA share one group when there are fewer groups than resident warps.
+
+__device__ __forceinline__ void csa(uint32_t &sum, uint32_t &carry, uint32_t a, uint32_t b, uint32_t c)
+{
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));   // majority
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));     // parity
+}
+
+struct Tree16 {
+    uint32_t ones = 0, twos = 0, fours = 0, eights = 0;
+    // adds 16 words, returns the weight-16 carry word
+    __device__ __forceinline__ uint32_t add(const uint32_t (&w)[16])
+    {
+        uint32_t t[8], f[4], e[2], s;
+#pragma unroll
+        for (int i = 0; i < 8; i++) csa(ones, t[i], ones, w[2 * i], w[2 * i + 1]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) csa(twos, f[i], twos, t[2 * i], t[2 * i + 1]);
+#pragma unroll
+        for (int i = 0; i < 2; i++) csa(fours, e[i], fours, f[2 * i], f[2 * i + 1]);
+        csa(eights, s, eights, e[0], e[1]);
+        return s;
+    }
+    // weighted popcount of the residual state under a mask
+    __device__ __forceinline__ uint32_t residual(uint32_t m) const
+    {
+        return 8u * __popc(eights & m) + 4u * __popc(fours & m) + 2u * __popc(twos & m) + __popc(ones & m);
+    }
+};
+
+template <int SPLIT>
+__global__ void __launch_bounds__(256)
+counts_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_t mc, int64_t n_samples,
+                 int32_t *__restrict__ counts, double *__restrict__ freq)
+{
+    __shared__ uint32_t part[8][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kGroupsPerCta = 8 / SPLIT;
+    const int sub = warp % SPLIT, gslot = warp / SPLIT;
+    const int64_t ngroups = (mc + 3) >> 2;
+    const int64_t nvec = (n_samples + 15) >> 4;            // 16-byte vectors holding samples
+    const int64_t nfull = nvec - 1;
+    const int tail_bytes = (int)(n_samples - 16 * nfull);  // 1..16 valid bytes in the last vector
+    const int64_t iters = (ngroups + (int64_t)gridDim.x * kGroupsPerCta - 1) / ((int64_t)gridDim.x * kGroupsPerCta);
+
+    for (int64_t it = 0; it < iters; it++) {
+        const int64_t g = (it * gridDim.x + blockIdx.x) * kGroupsPerCta + gslot;
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, both[4] = {0, 0, 0, 0};
+        if (g < ngroups) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(panel + g * group_stride);
+            Tree16 raw, bth;
+            for (int64_t i0 = sub * 32 + lane; i0 < nvec; i0 += 128 * SPLIT) {
+                uint32_t w[16];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int64_t i = i0 + (int64_t)q * 32 * SPLIT;
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < nvec) v = ldg_stream(p + i);
+                    if (i == nfull) {                       // samples >= N are never counted
+                        v.x &= word_mask(8 * (int64_t)tail_bytes, 0); v.y &= word_mask(8 * (int64_t)tail_bytes, 1);
+                        v.z &= word_mask(8 * (int64_t)tail_bytes, 2); v.w &= word_mask(8 * (int64_t)tail_bytes, 3);
+                    }
+                    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+                }
+                const uint32_t s = raw.add(w);
+#pragma unroll
+                for (int q = 0; q < 16; q++) w[q] &= w[q] >> 1;
+                const uint32_t sb = bth.add(w);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    lo[r] += __popc(s & (0x01010101u << (2 * r)));
+                    hi[r] += __popc(s & (0x02020202u << (2 * r)));
+                    both[r] += __popc(sb & (0x01010101u << (2 * r)));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                lo[r] = 16u * lo[r] + raw.residual(0x01010101u << (2 * r));
+                hi[r] = 16u * hi[r] + raw.residual(0x02020202u << (2 * r));
+                both[r] = 16u * both[r] + bth.residual(0x01010101u << (2 * r));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            lo[r] = __reduce_add_sync(0xFFFFFFFFu, lo[r]);
+            hi[r] = __reduce_add_sync(0xFFFFFFFFu, hi[r]);
+            both[r] = __reduce_add_sync(0xFFFFFFFFu, both[r]);
+        }
+        if (SPLIT > 1) {
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) { part[warp][r] = lo[r]; part[warp][4 + r] = hi[r]; part[warp][8 + r] = both[r]; }
+            }
+            __syncthreads();
+        }
+        if (sub == 0 && lane < 4 && g < ngroups) {
+            const int r = lane;
+            uint32_t l = 0, h = 0, b = 0;
+            if (SPLIT > 1) {
+                for (int q = 0; q < SPLIT; q++) { l += part[warp + q][r]; h += part[warp + q][4 + r]; b += part[warp + q][8 + r]; }
+            } else {
+                l = r == 0 ? lo[0] : r == 1 ? lo[1] : r == 2 ? lo[2] : lo[3];
+                h = r == 0 ? hi[0] : r == 1 ? hi[1] : r == 2 ? hi[2] : hi[3];
+                b = r == 0 ? both[0] : r == 1 ? both[1] : r == 2 ? both[2] : both[3];
+            }
+            const int64_t j = 4 * g + r;
+            if (j < mc) {
+                const int n2 = (int)b, n3 = (int)(l - b), n1 = (int)(h - b);
+                const int n0 = (int)n_samples - n1 - n2 - n3;
+                if (counts) reinterpret_cast<int4 *>(counts)[j] = make_int4(n0, n1, n2, n3);
+                if (freq) {
+                    const int nm = n2 + n1 + n0;               // source.cc:874
+                    freq[j] = (nm == 0) ? 0.0                  // source.cc:875
+                                        : static_cast<double>(2 * n0 + 1 * n1) / static_cast<double>(2 * nm);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts, double *d_freq)
 {
     if (mc <= 0) return SIMU_B200_OK;
     const int warps_per_block = 8;
-    int64_t blocks = (mc + warps_per_block - 1) / warps_per_block;
     const int64_t max_blocks = (int64_t)ctx->num_sms * 8;   // 64 resident warps per SM
-    if (blocks > max_blocks) blocks = max_blocks;
     const int ps = prof_begin(ctx, PROF_COUNTS);
-    counts_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>(
-        ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_counts, d_freq);
+    if (ctx->layout == SIMU_B200_LAYOUT_GROUP4) {
+        // one warp per 4-row group; when the groups do not fill the resident warps, 2/4/8 warps
+        // of a CTA share a group (more loads in flight per group row)
+        const int64_t groups = (mc + 3) >> 2;
+        const int64_t resident = max_blocks * warps_per_block;
+        int split = 1;
+        while (split < 8 && groups * split * 2 <= resident) split *= 2;
+        int64_t blocks = (groups * split + warps_per_block - 1) / warps_per_block;
+        if (blocks > max_blocks) blocks = max_blocks;
+#define LAUNCH_G4(S) counts_g4_kernel<S><<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>( \
+            ctx->panel, ctx->group_stride, mc, ctx->n_samples, d_counts, d_freq)
+        if (split == 1) LAUNCH_G4(1); else if (split == 2) LAUNCH_G4(2); else if (split == 4) LAUNCH_G4(4); else LAUNCH_G4(8);
+#undef LAUNCH_G4
+    } else {
+        int64_t blocks = (mc + warps_per_block - 1) / warps_per_block;
+        if (blocks > max_blocks) blocks = max_blocks;
+        counts_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>(
+            ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_counts, d_freq);
+    }
     prof_end(ctx, ps);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "counts_kernel launch");

@@ -21,6 +21,8 @@ struct simu_b200_ctx {
     int64_t row_stride = 0;   // pitch in HBM
     uint8_t *panel = nullptr;
     int64_t panel_rows = 0;
+    int layout = SIMU_B200_LAYOUT_ROWS;   // how the panel is laid out in HBM (simu_b200_layout)
+    int64_t group_stride = 0; // GROUP4: bytes per 4-row group = round_up(N, 128), one byte per sample
 
     cudaStream_t own_stream = nullptr;   // created by open
     cudaStream_t stream = nullptr;       // stream in use (own or external)
@@ -92,8 +94,14 @@ int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, c
                         const double *d_sumsq, double *d_coef);
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index);
 
-// staging: re-base contiguous rows to the panel pitch.  stage.cu
-int launch_repitch(simu_b200_ctx *ctx, const uint8_t *d_src, int64_t n_rows, int64_t dst_row, cudaStream_t stream);
+// staging: move n_rows packed rows (pitch src_pitch) from a device bounce buffer into panel rows
+// [dst_row, dst_row + n_rows) -- re-pitched (ROWS) or sample-interleaved (GROUP4).  stage.cu
+int launch_repitch(simu_b200_ctx *ctx, const uint8_t *d_src, int64_t src_pitch, int64_t n_rows, int64_t dst_row,
+                   cudaStream_t stream);
+// the inverse, for panel_get_rows: panel rows -> contiguous packed rows (pitch row_bytes).  stage.cu
+int launch_unpanel(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows, uint8_t *d_dst, cudaStream_t stream);
 
-// synthetic panel generator.  synth.cu
-int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, int64_t n_rows, int64_t dst_row);
+// synthetic panel generator: rows first_row + r (d_row_ids == NULL) or d_row_ids[r], r < n_rows, written
+// as packed rows at dst + r * dst_pitch (dst_pitch a multiple of 4).  synth.cu
+int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, const int64_t *d_row_ids, int64_t n_rows,
+                 uint8_t *dst, int64_t dst_pitch);

@@ -97,6 +97,89 @@ pheno_exact_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const 
     }
 }
 
+// GROUP4 layout: byte i of group g holds the 2-bit fields of sample i for rows 4g..4g+3, so a
+// thread reads ONE byte per sample per four SNPs and adds the four contributions in ascending
+// SNP order -- the same per-sample order as above, hence the same bits.
+template <int K, int SPT>
+__global__ void __launch_bounds__(kThreads)
+pheno_exact_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_t mc, int64_t n_samples,
+                      const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
+                      double *__restrict__ y1, double *__restrict__ y2)
+{
+    __shared__ double tbl[kChunk][4][K];      // [snp][raw bits][trait]
+    static_assert(SPT == 1 || SPT == 2 || SPT == 4, "SPT");
+    const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * SPT;
+    const bool active = first < n_samples;
+    const uint8_t *base = panel + (active ? first : 0);    // group_stride >= round_up(N, 128): SPT bytes are readable
+
+    double acc[SPT][K];
+#pragma unroll
+    for (int s = 0; s < SPT; s++)
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[s][k] = 0.0;
+
+    for (int64_t j0 = 0; j0 < mc; j0 += kChunk) {
+        const int nj = (int)min((int64_t)kChunk, mc - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nj; t += blockDim.x) {
+            const int64_t j = j0 + t;
+            const double avg = __dmul_rn(2.0, freq[j]);          // source.cc:986
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const double x = (k == 0) ? x1[j] : x2[j];
+                tbl[t][0][k] = __dmul_rn(__dsub_rn(2.0, avg), x);   // bits 00: two A1 copies
+                tbl[t][1][k] = 0.0;                                 // bits 01: missing (:991)
+                tbl[t][2][k] = __dmul_rn(__dsub_rn(1.0, avg), x);   // bits 10: one copy
+                tbl[t][3][k] = __dmul_rn(__dsub_rn(0.0, avg), x);   // bits 11: none
+            }
+        }
+        __syncthreads();
+        const int ng = (nj + 3) >> 2;                              // groups in this chunk (kChunk % 4 == 0)
+        const uint8_t *gp = base + (j0 >> 2) * group_stride;
+        constexpr int kAhead = 8;
+        for (int gg = 0; gg < ng; gg += kAhead) {
+            uint32_t b[kAhead];
+#pragma unroll
+            for (int u = 0; u < kAhead; u++) {
+                b[u] = 0u;
+                if (gg + u < ng) {
+                    const uint8_t *q = gp + (int64_t)(gg + u) * group_stride;
+                    if (SPT == 1) b[u] = __ldg(q);
+                    else if (SPT == 2) b[u] = __ldg(reinterpret_cast<const uint16_t *>(q));
+                    else b[u] = __ldg(reinterpret_cast<const uint32_t *>(q));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kAhead; u++) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int jj = 4 * (gg + u) + r;
+                    if (jj < nj) {
+#pragma unroll
+                        for (int s = 0; s < SPT; s++) {
+                            const uint32_t v = (b[u] >> (8 * s + 2 * r)) & 3u;
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                acc[s][k] = __dadd_rn(acc[s][k], tbl[jj][v][k]);   // source.cc:994-995
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (active) {
+#pragma unroll
+        for (int s = 0; s < SPT; s++) {
+            const int64_t i = first + s;
+            if (i < n_samples) {
+                y1[i] = acc[s][0];
+                if (K == 2) y2[i] = acc[s][K - 1];
+            }
+        }
+    }
+}
+
 template <int K, int SPT>
 void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq, const double *d_x1,
                     const double *d_x2, double *d_y1, double *d_y2)
@@ -107,8 +190,12 @@ void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const
     if (const char *e = getenv("SIMU_B200_EXACT_THREADS")) threads = atoi(e);
     const int64_t per_block = (int64_t)threads * SPT;
     const int64_t blocks = (ctx->n_samples + per_block - 1) / per_block;
-    pheno_exact_kernel<K, SPT><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
+    if (ctx->layout == SIMU_B200_LAYOUT_GROUP4)
+        pheno_exact_g4_kernel<K, SPT><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+            ctx->panel, ctx->group_stride, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
+    else
+        pheno_exact_kernel<K, SPT><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+            ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
 }
 
 }  // namespace

@@ -29,6 +29,8 @@
 // order, so the result is deterministic.
 //
 // Algorithmic bytes: Mc*(ceil(N/4) + 12 + 8K) + 8NK.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 namespace {
@@ -189,6 +191,35 @@ struct LutParams {
     int64_t steps;          // tiles * nblocks
 };
 
+// Every CTA walks its contiguous range of the (sample-tile major, row-block minor) step list in
+// ROTATED order: at local time it, it is at the step whose row block b satisfies b == it (mod len).
+// All CTAs (one per sample tile for any given block) therefore need the same ~nblocks/len table
+// blocks at the same time, so a table is fetched from HBM once and served to the other tiles' CTAs
+// from L2.  (tile, block) of the current step are carried along incrementally: 64-bit divisions
+// cost ~100 instructions each and used to be a quarter of all issued instructions.
+struct StepWalk {
+    struct Cursor { int64_t s, tile, blk; };
+    int64_t s_begin, s_end, len, nb, tile_b, blk_b;
+    Cursor first;
+    __device__ __forceinline__ StepWalk(const LutParams &p, int64_t cta, int64_t grid)
+    {
+        s_begin = (cta * p.steps) / grid; s_end = ((cta + 1) * p.steps) / grid;
+        len = s_end - s_begin;
+        nb = p.nblocks;
+        const int64_t rot = len > 0 ? (len - (s_begin - (s_begin / nb) * nb) % len) % len : 0;
+        tile_b = s_begin / nb; blk_b = s_begin - tile_b * nb;
+        first.s = s_begin + rot;
+        first.tile = tile_b + (blk_b + rot) / nb;
+        first.blk = (blk_b + rot) - (first.tile - tile_b) * nb;
+    }
+    __device__ __forceinline__ void advance(Cursor &c) const
+    {
+        c.s++; c.blk++;
+        if (c.blk == nb) { c.blk = 0; c.tile++; }
+        if (c.s == s_end) { c.s = s_begin; c.tile = tile_b; c.blk = blk_b; }
+    }
+};
+
 __device__ __forceinline__ int64_t cta_of_step(int64_t s, int64_t grid, int64_t steps)
 {
     return ((s + 1) * grid - 1) / steps;   // largest c with (c*steps)/grid <= s
@@ -258,27 +289,11 @@ pheno_lut_kernel(const LutParams p)
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t grid = gridDim.x, cta = blockIdx.x;
-    const int64_t s_begin = (cta * p.steps) / grid, s_end = ((cta + 1) * p.steps) / grid;
-    // Every CTA walks its contiguous range in ROTATED order: at local time it, it is at the step
-    // whose row block b satisfies b == it (mod len).  All CTAs (one per sample tile for any
-    // given block) therefore need the same ~nblocks/len table blocks at the same time, so a
-    // table is fetched from HBM once and served to the other tiles' CTAs from L2.
-    const int64_t len = s_end - s_begin;
-    const int64_t rot = len > 0 ? (len - (s_begin - (s_begin / p.nblocks) * p.nblocks) % len) % len : 0;
-    // (tile, block) of the current step are carried along incrementally: 64-bit divisions
-    // cost ~100 instructions each and used to be a quarter of all issued instructions.
-    const int64_t nb = p.nblocks;
-    const int64_t tile_b = s_begin / nb, blk_b = s_begin - tile_b * nb;
-    struct Cursor { int64_t s, tile, blk; };
-    Cursor first;
-    first.s = s_begin + rot;
-    first.tile = tile_b + (blk_b + rot) / nb;
-    first.blk = (blk_b + rot) - (first.tile - tile_b) * nb;
-    auto advance = [&](Cursor &c) {
-        c.s++; c.blk++;
-        if (c.blk == nb) { c.blk = 0; c.tile++; }
-        if (c.s == s_end) { c.s = s_begin; c.tile = tile_b; c.blk = blk_b; }
-    };
+    StepWalk walk(p, cta, grid);
+    const int64_t len = walk.len;
+    typedef StepWalk::Cursor Cursor;
+    const Cursor first = walk.first;
+    auto advance = [&](Cursor &c) { walk.advance(c); };
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_base + kStages * kStageBytes;
@@ -408,6 +423,179 @@ pheno_lut_kernel(const LutParams p)
         flush_acc<K>(acc, p.ypart, p.npad, slot, cur_tile * kTileSamples + warp * 512 + lane * 16);
 }
 
+// ---------------------------------------------------------------- GROUP4 panel layout
+//
+// In a GROUP4 panel four consecutive SNP rows are stored sample-interleaved: byte i of group g
+// holds the 2-bit fields of sample i for rows 4g..4g+3 (row 4g in bits 0-1) -- which IS the
+// table index e.  The kernel then needs no bit transposition at all: a lane reads its 16
+// samples of a group with ONE 16-byte shared-memory load and goes straight to the lookups
+// (44 instead of ~70 instructions per 64 genotypes), and a step is 16 bulk copies of 4 KB
+// instead of 64 of 1 KB.  SPLIT = 2 runs two consumer warps per 512-sample column set, each
+// taking every other sub-step (16 consumer warps: more latency hiding when the shared-memory
+// pipe is not yet the limit, K = 1), flushing into separate FP64 slots.
+constexpr int kG4TileBytes = kTileSamples;           // 4096: one byte per sample per group
+
+template <int SPLIT> struct G4Shape {
+    static constexpr int kConsumers = kWarps * SPLIT;
+    static constexpr int kThreads = (kConsumers + 1) * 32;      // + one producer warp
+    static constexpr int kSmemBytes = kStages * kStageBytes + 64;
+};
+
+template <int K>
+__device__ __forceinline__ void lookup4_g4(float2 (&acc)[8 * K], const uint32_t z, const uint32_t tbl, const int w)
+{
+    // bytes 0..3 of z are the table indices of samples 4w .. 4w+3
+    uint32_t a[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) a[m] = __dp4a(z, 0x80u << (8 * m), tbl);
+    if (K == 1) {
+        float v[4];
+#pragma unroll
+        for (int m = 0; m < 4; m++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[m]) : "r"(a[m]));
+        acc[2 * w + 0] = __fadd2_rn(acc[2 * w + 0], make_float2(v[0], v[1]));
+        acc[2 * w + 1] = __fadd2_rn(acc[2 * w + 1], make_float2(v[2], v[3]));
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            float2 v;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a[m]));
+            acc[4 * w + m] = __fadd2_rn(acc[4 * w + m], v);
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void flush_acc_g4(float2 (&acc)[8 * K], double *__restrict__ ypart, int64_t npad,
+                                             int64_t slot, int64_t sample0)
+{
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double *dst = ypart + (slot * K + k) * npad + sample0;
+#pragma unroll
+        for (int s = 0; s < 16; s += 2) {
+            double2 v = *reinterpret_cast<double2 *>(dst + s);
+            if (K == 1) { v.x += (double)acc[s >> 1].x; v.y += (double)acc[s >> 1].y; }
+            else { v.x += (double)(k == 0 ? acc[s].x : acc[s].y); v.y += (double)(k == 0 ? acc[s + 1].x : acc[s + 1].y); }
+            *reinterpret_cast<double2 *>(dst + s) = v;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8 * K; i++) acc[i] = make_float2(0.f, 0.f);
+}
+
+template <int K, int SPLIT>
+__global__ void __launch_bounds__(G4Shape<SPLIT>::kThreads, 1)
+pheno_lut_g4_kernel(const LutParams p)
+{
+    constexpr int kConsumers = G4Shape<SPLIT>::kConsumers;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t grid = gridDim.x, cta = blockIdx.x;
+    StepWalk walk(p, cta, grid);
+    const int64_t len = walk.len;
+    typedef StepWalk::Cursor Cursor;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_base + kStages * kStageBytes;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(bar_base + 8 * s, 1);
+            mbar_init(bar_base + 16 + 8 * s, kConsumers);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t gstride = p.row_stride;            // bytes per 4-row group (>= N, multiple of 128)
+    const int64_t ngroups_total = (p.mc + 3) >> 2;
+
+    if (warp == kConsumers) {
+        // ============ producer warp: lane g copies group g's 4 KB slice, lane 16 the table ============
+        uint64_t pol_stream, pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        Cursor c = walk.first;
+        for (int64_t it = 0; it < len; it++) {
+            const int stage = (int)(it & 1);
+            const uint32_t parity = (uint32_t)((it >> 1) & 1);
+            const uint32_t full = bar_base + 8 * stage, empty = bar_base + 16 + 8 * stage;
+            const uint32_t stage_base = smem_base + stage * kStageBytes;
+            const int64_t tile = c.tile, blk = c.blk;
+            const uint32_t bytes = (uint32_t)min((int64_t)kG4TileBytes, gstride - tile * kG4TileBytes);
+            const int ng = (int)min((int64_t)kGroups, ngroups_total - blk * kGroups);
+            const uint8_t *src = p.panel + (blk * kGroups + (lane & 15)) * gstride + tile * kG4TileBytes;
+            walk.advance(c);
+            if (it + 1 < len) {
+                // pull the next step's slices into L2 one whole step ahead (2 lanes per group)
+                const int ngn = (int)min((int64_t)kGroups, ngroups_total - c.blk * kGroups);
+                if ((lane & 15) < ngn) {
+                    const uint8_t *nx = p.panel + (c.blk * kGroups + (lane & 15)) * gstride + c.tile * kG4TileBytes;
+                    const int nlines = (int)(min((int64_t)kG4TileBytes, gstride - c.tile * kG4TileBytes) >> 7);
+                    for (int q = (lane >> 4); q < nlines; q += 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + q * 128));
+                }
+            }
+            if (lane == 0) {
+                mbar_wait_backoff(empty, parity ^ 1u);
+                mbar_arrive_expect_tx(full, (uint32_t)ng * bytes + (uint32_t)kTableBytes);
+            }
+            __syncwarp();
+            if (lane < ng) bulk_g2s(stage_base + lane * kG4TileBytes, src, bytes, full, pol_stream);
+            else if (lane == 16)
+                bulk_g2s(stage_base + kGroups * kG4TileBytes, p.lut + blk * (kTableBytes / 4), kTableBytes, full, pol_keep);
+        }
+        return;
+    }
+
+    // ========================= consumer warps: lookups =========================
+    const int cw = warp % kWarps, half = warp / kWarps;       // column set, sub-step parity
+    float2 acc[8 * K];
+#pragma unroll
+    for (int i = 0; i < 8 * K; i++) acc[i] = make_float2(0.f, 0.f);
+
+    int64_t cur_tile = -1, slot = 0;
+    int since_flush = 0;
+    Cursor cc = walk.first;
+    for (int64_t it = 0; it < len; it++, walk.advance(cc)) {
+        const int stage = (int)(it & 1);
+        const uint32_t parity = (uint32_t)((it >> 1) & 1);
+        const int64_t tile = cc.tile;
+        if (tile != cur_tile || since_flush == kFlushBlocks * SPLIT) {
+            if (cur_tile >= 0)
+                flush_acc_g4<K>(acc, p.ypart, p.npad, slot, cur_tile * kTileSamples + cw * 512 + lane * 16);
+            if (tile != cur_tile) {
+                cur_tile = tile;
+                slot = (cta - cta_of_step(tile * p.nblocks, grid, p.steps)) * SPLIT + half;
+            }
+            since_flush = 0;
+        }
+        since_flush++;
+
+        const uint32_t full = bar_base + 8 * stage, empty = bar_base + 16 + 8 * stage;
+        const uint32_t stage_base = smem_base + stage * kStageBytes;
+        const uint32_t mine = stage_base + cw * 512 + lane * 16;            // this lane's 16 samples, group 0
+        const uint32_t table = stage_base + kGroups * kG4TileBytes;
+        mbar_wait(full, parity);
+
+#pragma unroll kUnroll
+        for (int i = 0; i < kGroups / SPLIT; i++) {
+            const int t = i * SPLIT + half;
+            const uint32_t gi = (uint32_t)(lane + t) & 15u;
+            uint32_t z0, z1, z2, z3;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(z0), "=r"(z1), "=r"(z2), "=r"(z3)
+                         : "r"(mine + gi * kG4TileBytes));
+            const uint32_t tbl = table + (K == 1 ? (gi + (lane & 16u)) * 4u : gi * 8u);
+            lookup4_g4<K>(acc, z0, tbl, 0);
+            lookup4_g4<K>(acc, z1, tbl, 1);
+            lookup4_g4<K>(acc, z2, tbl, 2);
+            lookup4_g4<K>(acc, z3, tbl, 3);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty);
+    }
+    if (cur_tile >= 0)
+        flush_acc_g4<K>(acc, p.ypart, p.npad, slot, cur_tile * kTileSamples + cw * 512 + lane * 16);
+}
+
 // y[k][i] = sum over the slots of the tile that holds sample i, in slot order
 template <int K>
 __global__ void __launch_bounds__(256)
@@ -433,16 +621,26 @@ int run_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double 
     const int64_t nblocks = (mc + kBlockRows - 1) / kBlockRows;
     const int64_t steps = tiles * nblocks;
     const int64_t grid = steps < ctx->num_sms ? steps : ctx->num_sms;
-    const int slots = (int)((grid + tiles - 1) / tiles) + 1;
+    const int slots1 = (int)((grid + tiles - 1) / tiles) + 1;
     const int64_t npad = tiles * kTileSamples;
 
     float *lut = (float *)ctx_scratch(ctx, SCR_LUT, (size_t)nblocks * kTableBytes);
+
+    // GROUP4 panels: K = 1 runs two consumer warps per column set (measured on config 4: 8.30 ms
+    // row-major -> 6.96 ms GROUP4 -> 6.66 ms with the split); K = 2 sits on the shared-memory pipe
+    // either way and keeps 8 consumer warps.  SIMU_B200_LUT_SPLIT=1|2 overrides for A/B runs.
+    const bool g4 = ctx->layout == SIMU_B200_LAYOUT_GROUP4;
+    int split = (g4 && K == 1) ? 2 : 1;
+    if (const char *e = getenv("SIMU_B200_LUT_SPLIT")) { if (g4 && K == 1) split = atoi(e) == 1 ? 1 : 2; }
+    const int slots = slots1 * split;
     const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
     double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
     if (!lut || !ypart) return SIMU_B200_ENOMEM;
-
     if (!ctx->lut_attr_set[K]) {   // per context: the attribute is per device
         CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_g4_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4Shape<1>::kSmemBytes));
+        if (K == 1)
+            CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_g4_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4Shape<2>::kSmemBytes));
         ctx->lut_attr_set[K] = true;
     }
     CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
@@ -451,10 +649,17 @@ int run_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double 
     prof_end(ctx, ps);
 
     LutParams p;
-    p.panel = ctx->panel; p.row_stride = ctx->row_stride; p.rows = d_rows; p.mc = mc; p.n_samples = n;
-    p.lut = lut; p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
+    p.panel = ctx->panel; p.row_stride = g4 ? ctx->group_stride : ctx->row_stride; p.rows = d_rows; p.mc = mc;
+    p.n_samples = n; p.lut = lut; p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
     ps = prof_begin(ctx, PROF_LUT_MAIN);
-    pheno_lut_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p);
+    if (g4) {
+        if (K == 1 && split == 2)
+            pheno_lut_g4_kernel<1, 2><<<(unsigned)grid, G4Shape<2>::kThreads, G4Shape<2>::kSmemBytes, ctx->stream>>>(p);
+        else
+            pheno_lut_g4_kernel<K, 1><<<(unsigned)grid, G4Shape<1>::kThreads, G4Shape<1>::kSmemBytes, ctx->stream>>>(p);
+    } else {
+        pheno_lut_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p);
+    }
     prof_end(ctx, ps);
     ps = prof_begin(ctx, PROF_LUT_REDUCE);
     lut_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, d_y1, d_y2);

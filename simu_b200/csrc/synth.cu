@@ -25,15 +25,15 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z)
 }
 
 __global__ void __launch_bounds__(256)
-synth_kernel(uint8_t *__restrict__ panel, int64_t row_stride, int64_t n_samples, uint64_t seed,
-             int64_t first_row, int64_t n_rows, int64_t dst_row)
+synth_kernel(uint8_t *__restrict__ dst, int64_t row_stride, int64_t n_samples, uint64_t seed,
+             int64_t first_row, const int64_t *__restrict__ row_ids, int64_t n_rows)
 {
     const int64_t words_per_row = row_stride >> 2;
     const int64_t total = n_rows * words_per_row;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = t / words_per_row, w = t - r * words_per_row;
-        const uint64_t key = mix64(seed ^ mix64((uint64_t)(first_row + r)));
+        const uint64_t key = mix64(seed ^ mix64((uint64_t)(row_ids ? row_ids[r] : first_row + r)));
         const uint32_t thr = 10486u + (uint32_t)(((key >> 32) * 513802ull) >> 32);
         uint32_t word = 0;
 #pragma unroll
@@ -48,21 +48,22 @@ synth_kernel(uint8_t *__restrict__ panel, int64_t row_stride, int64_t n_samples,
                 word |= bits << (2 * s);
             }
         }
-        reinterpret_cast<uint32_t *>(panel + (dst_row + r) * row_stride)[w] = word;
+        reinterpret_cast<uint32_t *>(dst + r * row_stride)[w] = word;
     }
 }
 
 }  // namespace
 
-int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, int64_t n_rows, int64_t dst_row)
+int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, const int64_t *d_row_ids, int64_t n_rows,
+                 uint8_t *dst, int64_t dst_pitch)
 {
     if (n_rows <= 0) return SIMU_B200_OK;
-    const int64_t total = n_rows * (ctx->row_stride >> 2);
+    const int64_t total = n_rows * (dst_pitch >> 2);
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = (int64_t)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;
-    synth_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(ctx->panel, ctx->row_stride, ctx->n_samples, seed,
-                                                            first_row, n_rows, dst_row);
+    synth_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(dst, dst_pitch, ctx->n_samples, seed, first_row, d_row_ids,
+                                                            n_rows);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "synth_kernel launch");
 }

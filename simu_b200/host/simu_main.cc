@@ -465,7 +465,9 @@ struct Gpu {
         causal.clear();
         for (int v = 0; v < o.num_variants; v++)
             if (comp[v] != -1) causal.push_back(v);
-        check(simu_b200_panel_alloc(ctx, std::max<size_t>(1, causal.size())));
+        // compact causal panel (only the rows pio_next_row would read), sample-interleaved in groups of four
+        // rows so that find_pheno's FAST kernel reads its table index directly
+        check(simu_b200_panel_alloc_layout(ctx, std::max<size_t>(1, causal.size()), SIMU_B200_LAYOUT_GROUP4));
         size_t pos = 0;
         int64_t dst = 0;
         for (size_t f = 0; f < pio.num_files(); f++) {

@@ -158,7 +158,8 @@ class PlinkFiles:
         if v.size and np.any(np.diff(v) <= 0):
             raise ValueError("variant_indices must be strictly ascending")
         if ctx.panel_rows < max(1, v.size):
-            ctx.panel_alloc(max(1, v.size))
+            from . import capi                   # compact causal panel -> sample-interleaved groups of 4 rows
+            ctx.panel_alloc(max(1, v.size), capi.LAYOUT_GROUP4)
         dst = 0
         for f, local in self.split_by_file(v):
             ctx.panel_load_bed(self.files[f].bed_path, self.files[f].num_loci, local, dst_row=dst)

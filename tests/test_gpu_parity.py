@@ -19,6 +19,8 @@ pytestmark = pytest.mark.gpu
 
 PANEL_SEED = 20240901
 FAST_RTOL = 1e-5
+# every test that does not address rows through a row list runs on both panel layouts
+LAYOUTS = pytest.mark.parametrize("layout", [capi.LAYOUT_ROWS, capi.LAYOUT_GROUP4], ids=["rows", "group4"])
 
 
 def _effects(mc, seed, k2=True):
@@ -34,10 +36,11 @@ def _panel(n, m):
 
 # ------------------------------------------------------------------ golden
 
-def test_golden_rows_through_the_abi():
+@LAYOUTS
+def test_golden_rows_through_the_abi(layout):
     """bed_test.c:237-329 vectors: 0x78 -> [0,1,2,3], 0x2d -> [3,2,1,0]."""
     with capi.Context(4) as ctx:
-        ctx.panel_alloc(2)
+        ctx.panel_alloc(2, layout)
         ctx.panel_put_rows(0, np.array([[0x78], [0x2D]], np.uint8))
         counts, freq = ctx.find_freq()
         assert counts.tolist() == [[1, 1, 1, 1], [1, 1, 1, 1]]
@@ -48,10 +51,11 @@ def test_golden_rows_through_the_abi():
             assert y2.tolist() == [2.0, 1.0, -2.0, -1.0]
 
 
-def test_synth_generator_matches_host():
+@LAYOUTS
+def test_synth_generator_matches_host(layout):
     n, m = 1003, 37
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(m)
+        ctx.panel_alloc(m, layout)
         ctx.panel_synth(PANEL_SEED, 5, m)
         dev = ctx.panel_get_rows(0, m)
     assert np.array_equal(dev, oracle.synth_rows(PANEL_SEED, 5, m, n))
@@ -60,11 +64,12 @@ def test_synth_generator_matches_host():
 # ------------------------------------------------------------------ counts
 
 @pytest.mark.parametrize("n", [1, 3, 4, 5, 63, 64, 65, 127, 128, 129, 511, 513, 1000, 4097, 10000, 33333])
-def test_counts_bit_exact_ragged_n(n):
+@LAYOUTS
+def test_counts_bit_exact_ragged_n(n, layout):
     m = 41
     rows = _panel(n, m)
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(m)
+        ctx.panel_alloc(m, layout)
         ctx.panel_put_rows(0, rows)
         counts, freq = ctx.find_freq()
     oc, of = oracle.find_freq(rows, n)
@@ -72,7 +77,8 @@ def test_counts_bit_exact_ragged_n(n):
     assert np.array_equal(freq, of)          # same IEEE expression -> same bits
 
 
-def test_counts_ignore_padding_garbage_and_handle_all_missing():
+@LAYOUTS
+def test_counts_ignore_padding_garbage_and_handle_all_missing(layout):
     n = 13
     rows = _panel(n, 6)
     B = plink.row_bytes(n)
@@ -81,7 +87,7 @@ def test_counts_ignore_padding_garbage_and_handle_all_missing():
     wide = np.full((6, B + 9), 0xFF, np.uint8)   # host stride > row bytes, garbage beyond
     wide[:, :B] = rows
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(6)
+        ctx.panel_alloc(6, layout)
         ctx.panel_put_rows(0, wide)
         counts, freq = ctx.find_freq()
     oc, of = oracle.find_freq(rows, n)
@@ -105,12 +111,13 @@ def test_counts_gather_by_row_list():
 
 @pytest.mark.parametrize("n,mc,k2", [(1, 5, False), (7, 1, True), (64, 64, True), (257, 130, False),
                                      (1000, 333, True), (4099, 257, True), (10000, 1000, False)])
-def test_pheno_exact_bit_identical(n, mc, k2):
+@LAYOUTS
+def test_pheno_exact_bit_identical(n, mc, k2, layout):
     rows = _panel(n, mc)
     _, freq = oracle.find_freq(rows, n)
     x1, x2 = _effects(mc, n + mc, k2)
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc)
+        ctx.panel_alloc(mc, layout)
         ctx.panel_put_rows(0, rows)
         y1, y2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_EXACT)
     o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2)
@@ -122,12 +129,13 @@ def test_pheno_exact_bit_identical(n, mc, k2):
 @pytest.mark.parametrize("n,mc,k2", [(1, 5, False), (7, 1, True), (64, 64, True), (257, 130, False),
                                      (1000, 333, True), (4099, 257, True), (10000, 1000, False),
                                      (9001, 4100, True), (20000, 3000, False)])
-def test_pheno_fast_within_tolerance(n, mc, k2):
+@LAYOUTS
+def test_pheno_fast_within_tolerance(n, mc, k2, layout):
     rows = _panel(n, mc)
     _, freq = oracle.find_freq(rows, n)
     x1, x2 = _effects(mc, 3 * n + mc, k2)
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc)
+        ctx.panel_alloc(mc, layout)
         ctx.panel_put_rows(0, rows)
         y1, y2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
     o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2)
@@ -163,9 +171,10 @@ def test_pheno_gather_missing_and_scaled_effects(mode):
         assert np.max(np.abs(y2 - o2)) <= FAST_RTOL * np.max(np.abs(o2))
 
 
-def test_pheno_empty_causal_set():
+@LAYOUTS
+def test_pheno_empty_causal_set(layout):
     with capi.Context(10) as ctx:
-        ctx.panel_alloc(1)
+        ctx.panel_alloc(1, layout)
         y1, y2 = ctx.find_pheno(np.zeros(0), np.zeros(0), np.zeros(0))
         assert not y1.any() and not y2.any()
         counts, freq = ctx.find_freq(mc=0)
@@ -173,12 +182,13 @@ def test_pheno_empty_causal_set():
 
 
 @pytest.mark.parametrize("mode", [capi.MODE_EXACT, capi.MODE_FAST])
-def test_pheno_linearity_property_config1_shape(mode):
+@LAYOUTS
+def test_pheno_linearity_property_config1_shape(mode, layout):
     """Size-independent property at config-1 shape (10K x 1000 causal):
     y(x_a + x_b) == y(x_a) + y(x_b) and y(c x) == c y(x) up to rounding."""
     n, mc = 10000, 1000
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc)
+        ctx.panel_alloc(mc, layout)
         ctx.panel_synth(PANEL_SEED, 0, mc)
         _, freq = ctx.find_freq()
         xa, xb = _effects(mc, 11, True)
@@ -191,6 +201,85 @@ def test_pheno_linearity_property_config1_shape(mode):
     # centred genotypes: sum_i y_i == -sum_j 2 f_j x_j m_j ... for SNPs without missing data the
     # column of centred dosages sums to zero, so |mean(y)| stays tiny next to |y|
     assert abs(ya.mean()) < 0.05 * np.abs(ya).max()
+
+
+# ------------------------------------------------------------ GROUP4 layout
+
+def test_group4_append_at_any_offset_and_read_back():
+    """Rows appended in pieces that do not end on group boundaries (three bfiles of 5, 1 and 13
+    causal rows, say) interleave into the same panel as one put; get_rows undoes the layout."""
+    n, m = 1001, 19
+    rows = _panel(n, m)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m, capi.LAYOUT_GROUP4)
+        assert ctx.layout == capi.LAYOUT_GROUP4 and ctx.group_stride == 1024
+        for lo, hi in ((0, 5), (5, 6), (6, 19)):
+            ctx.panel_put_rows(lo, rows[lo:hi])
+        assert np.array_equal(ctx.panel_get_rows(0, m), rows)
+        assert np.array_equal(ctx.panel_get_rows(3, 7), rows[3:10])
+        counts, freq = ctx.find_freq()
+        # overwrite two rows in the middle of groups: the neighbours keep their bits
+        ctx.panel_put_rows(6, rows[0:2])
+        back = ctx.panel_get_rows(0, m)
+    oc, of = oracle.find_freq(rows, n)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+    expect = rows.copy(); expect[6:8] = rows[0:2]
+    assert np.array_equal(back, expect)
+
+
+def test_group4_byte_is_the_table_index():
+    """Layout contract: byte i of group g = fields of sample i for rows 4g..4g+3, row 4g lowest."""
+    import torch
+    n, m = 300, 8
+    rows = _panel(n, m)
+    codes = np.stack([(rows[j, np.arange(n) // 4] >> (2 * (np.arange(n) % 4))) & 3 for j in range(m)])
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m, capi.LAYOUT_GROUP4)
+        ctx.panel_put_rows(0, rows)
+        ctx.sync()
+        gs = ctx.group_stride
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (2, gs), "typestr": "|u1", "data": (ctx.panel_ptr, False), "version": 2,
+                                        "strides": None}
+        raw = torch.as_tensor(_Mem(), device="cuda").cpu().numpy()
+    for g in range(2):
+        want = codes[4 * g] | (codes[4 * g + 1] << 2) | (codes[4 * g + 2] << 4) | (codes[4 * g + 3] << 6)
+        assert np.array_equal(raw[g, :n], want.astype(np.uint8))
+
+
+def test_group4_rejects_row_lists():
+    with capi.Context(100) as ctx:
+        ctx.panel_alloc(8, capi.LAYOUT_GROUP4)
+        with pytest.raises(capi.SimuB200Error) as ei:
+            ctx.find_freq(rows=np.array([1, 2], np.int32))
+        assert ei.value.status == capi.EINVAL and "GROUP4" in str(ei.value)
+        with pytest.raises(capi.SimuB200Error):
+            ctx.find_pheno(np.zeros(2), np.zeros(2), rows=np.array([1, 2], np.int32))
+
+
+@LAYOUTS
+def test_synth_rows_scattered(layout):
+    n = 777
+    ids = np.array([3, 4, 5, 100, 2_000_000, 7], np.int64)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(10, layout)
+        ctx.panel_synth_rows(PANEL_SEED, ids, dst_row=3)
+        dev = ctx.panel_get_rows(3, ids.size)
+    want = np.concatenate([oracle.synth_rows(PANEL_SEED, int(r), 1, n) for r in ids])
+    assert np.array_equal(dev, want)
+
+
+@pytest.mark.parametrize("n,mc", [(100_000, 9), (100_000, 700), (40_000, 5000), (5, 4000)])
+def test_group4_counts_warp_split_paths(n, mc):
+    """few groups x long rows -> 8/4/2 warps share a group; many groups -> one warp each."""
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        ctx.panel_synth(PANEL_SEED, 11, mc)
+        counts, freq = ctx.find_freq()
+        rows = ctx.panel_get_rows(0, mc)
+    oc, of = oracle.find_freq(rows, n)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
 
 
 # ---------------------------------------------------------------- kernel (c)
@@ -258,14 +347,15 @@ def test_liability_threshold_labels_agree_with_oracle():
 
 # ------------------------------------------------------- staging from .bed
 
-def test_load_bed_causal_rows_only(tmp_path):
+@LAYOUTS
+def test_load_bed_causal_rows_only(tmp_path, layout):
     n, m = 777, 120
     rows = _panel(n, m)
     prefix = str(tmp_path / "syn")
     plink.write_fileset(prefix, rows, n)
     sel = np.sort(np.random.default_rng(2).choice(m, 40, replace=False))
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(40)
+        ctx.panel_alloc(40, layout)
         ctx.panel_load_bed(prefix + ".bed", m, sel)
         assert np.array_equal(ctx.panel_get_rows(0, 40), rows[sel])
         counts, _ = ctx.find_freq()
