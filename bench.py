@@ -10,8 +10,10 @@ One "step" = one pass of the hot path over one batch of synthetic input:
 Metric (BASELINE.json): genotype x effect updates per second = N * Mc * K per
 step, whole job over all GPUs; packed-.bed GB/s and the HBM roofline fraction of
 the dominant kernel ride along.  Default workload = BASELINE configs[1]:
-100K individuals x 1M SNPs resident in HBM (25 GB), 100K causal SNPs, 2 traits,
---gcta-sigma effects.  Data is synthetic (SURVEY.md 8d generator, panel seed
+100K individuals x 1M SNPs, 100K causal SNPs, 2 traits, --gcta-sigma effects; the
+causal rows (2.5 GB, all the reference ever reads) are resident in HBM as a compact
+GROUP4 panel, as the drop-in CLI stages them (--layout rows: the whole 25 GB slice
+row-major + a causal row list).  Data is synthetic (SURVEY.md 8d generator, panel seed
 20240901) and generated on the device.
 
 `--impl reference` times the reference's CPU algorithm (the oracle port of
@@ -58,11 +60,11 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def _traffic(workload, kernel):
+def _traffic(workload, kernel, layout="rows"):
     """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), or None."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        return t[workload][kernel]["dram_bytes_per_launch"]
+        return t[workload if layout == "rows" else f"{workload}:{layout}"][kernel]["dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -256,10 +258,22 @@ def run_ours(args, w):
     stream = torch.cuda.Stream(device=dev)           # one stream for torch ops, NCCL hand-off and our kernels
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    ctx.panel_alloc(m)
-    ctx.panel_synth(PANEL_SEED, rank * m, m)        # each GPU holds its own slice of the panel
     causal = _causal_rows(w, rank)
-    d_rows = torch.from_numpy(causal).to(dev) if mc != m else None
+    g4 = args.layout == "group4"
+    if g4:
+        # what the drop-in CLI keeps in HBM: the causal rows only (the reference reads no others,
+        # source.cc:852-863), compact and in causal order, four rows sample-interleaved per group
+        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        if mc == m:
+            ctx.panel_synth(PANEL_SEED, rank * m, m)
+        else:
+            ctx.panel_synth_rows(PANEL_SEED, causal.astype(np.int64) + rank * m)
+        d_rows = None
+    else:
+        # the whole slice of the .bed resident, row-major; causal rows gathered through a row list
+        ctx.panel_alloc(m)
+        ctx.panel_synth(PANEL_SEED, rank * m, m)        # each GPU holds its own slice of the panel
+        d_rows = torch.from_numpy(causal).to(dev) if mc != m else None
     rows_ptr = d_rows.data_ptr() if d_rows is not None else 0
     d_counts = torch.empty((mc, 4), dtype=torch.int32, device=dev)
     d_freq = torch.empty(mc, dtype=torch.float64, device=dev)
@@ -336,17 +350,20 @@ def run_ours(args, w):
 
     # ------------------------------------------------ e2e through the host-buffer C ABI
     e2e_steps = max(2, min(args.steps, 5))
-    panel_view = torch.as_tensor(_DevMem(ctx.panel_ptr, (m, ctx.row_stride)), device=dev)
-    host_rows = torch.empty((mc, B), dtype=torch.uint8, pin_memory=True)
-    chunk = max(1, (1 << 30) // ctx.row_stride)
-    for lo in range(0, mc, chunk):
-        hi = min(mc, lo + chunk)
-        idx = torch.from_numpy(causal[lo:hi].astype(np.int64)).to(dev)
-        host_rows[lo:hi].copy_(panel_view.index_select(0, idx)[:, :B])
-    torch.cuda.synchronize()
-    del panel_view
+    host_rows = torch.empty((mc, B), dtype=torch.uint8, pin_memory=True)     # the causal rows as packed .bed rows
+    if g4:
+        ctx.panel_get_rows_ptr(0, mc, host_rows.data_ptr(), B)
+    else:
+        panel_view = torch.as_tensor(_DevMem(ctx.panel_ptr, (m, ctx.row_stride)), device=dev)
+        chunk = max(1, (1 << 30) // ctx.row_stride)
+        for lo in range(0, mc, chunk):
+            hi = min(mc, lo + chunk)
+            idx = torch.from_numpy(causal[lo:hi].astype(np.int64)).to(dev)
+            host_rows[lo:hi].copy_(panel_view.index_select(0, idx)[:, :B])
+        torch.cuda.synchronize()
+        del panel_view
     ctx2 = capi.Context(n, device=local)
-    ctx2.panel_alloc(mc)
+    ctx2.panel_alloc(mc, capi.LAYOUT_GROUP4 if g4 else capi.LAYOUT_ROWS)
     noise_h = d_noise.cpu().numpy()
     e2e_y = None
 
@@ -412,16 +429,17 @@ def run_ours(args, w):
         roof = None
         if main_n:
             ach = bytes_pheno / (main_ms / main_n * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel",
+            sfx = "_g4_kernel" if g4 else "_kernel"
+            roof = {"bound": "hbm", "kernel": ("pheno_lut" if mode == capi.MODE_FAST else "pheno_exact") + sfx,
                     "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": _traffic(args.workload, "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel"),
+                    "traffic": _traffic(args.workload, "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel", args.layout),
                     "peak_source": peak_src, "ms_per_launch": main_ms / main_n,
                     "algorithmic_bytes_per_launch": bytes_pheno, "launches_timed": main_n}
         counts_roof = None
         if cnt_n:
             ach = bytes_counts / (cnt_ms / cnt_n * 1e-3) / 1e9
-            counts_roof = {"kernel": "counts_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": ach / peaks["hbm_gbs"], "traffic": _traffic(args.workload, "counts_kernel"),
+            counts_roof = {"kernel": "counts_g4_kernel" if g4 else "counts_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": ach / peaks["hbm_gbs"], "traffic": _traffic(args.workload, "counts_kernel", args.layout),
                            "ms_per_launch": cnt_ms / cnt_n,
                            "algorithmic_bytes_per_launch": bytes_counts}
         line = {
@@ -431,6 +449,8 @@ def run_ours(args, w):
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": w["desc"], "n_samples": n, "panel_rows_per_gpu": m,
                        "n_causal_per_gpu": mc, "traits": k, "mode": args.mode,
+                       "hbm_panel": ("causal rows only, compact, GROUP4 (4 rows sample-interleaved)" if g4 else
+                                     "whole .bed slice row-major + causal row list"),
                        "l2": f"inputs larger than L2 ({mc * B / 1e6:.0f} MB of causal rows per pass, 126 MB L2)",
                        "parallelism": f"snp-shard x{world}, 1 all-reduce" if world > 1 else "single GPU"},
             "bed_gbs": 2 * mc * B * world / (ms_step * 1e-3) / 1e9,
@@ -478,6 +498,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--layout", default="group4", choices=["group4", "rows"],
+                    help="HBM panel: compact causal rows in GROUP4 layout (what the CLI stages) or the whole "
+                         ".bed slice row-major with a causal row list")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()

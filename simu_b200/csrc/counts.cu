@@ -16,6 +16,8 @@
 // __reduce_add_sync.
 //
 // Algorithmic bytes per SNP: ceil(N/4) read + 16 (counts) + 8 (freq) written.
+#include <type_traits>
+
 #include "ctx.cuh"
 
 namespace {
@@ -115,38 +117,56 @@ counts_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32
 //
 // In a GROUP4 panel a 32-bit word holds 4 samples x 4 SNP rows (row r of the group in bits
 // 8s+2r, 8s+2r+1), so ONE pass over a group yields the counts of its four SNPs: the words go
-// through the same carry-save tree, only the final POPCs are taken under per-row masks.  The
-// tree is one level deeper than above (ones/twos/fours/eights, POPC of the weight-16 word:
-// 12 POPC per 256 genotypes) because there are 12 masked POPCs per tree output instead of 2.
-// The lo&hi plane is fed into a second tree as w & (w >> 1): its odd bits are garbage, but
-// carry-save adders are bitwise, so they never reach the even bits the masks select.
+// through the same kind of carry-save tree, only the final POPCs are taken under per-row masks.
+// LOP3 / SHF issue on the half-rate ALU pipe (64 lanes/clk/SM), which makes this kernel
+// ALU-bound long before it is HBM-bound unless the logic per word is kept near the tree's
+// inherent 2 LOP3 per word and plane:
+//   * the tree is 5 levels deep (ones .. sixteens, POPC of the weight-32 carry word), so the 12
+//     masked POPCs (4 rows x {lo, hi, lo&hi}) are paid once per 32 words = 512 genotypes;
+//   * the lo&hi plane is fed into a second tree as w & (w << 1) -- the shift is an IMAD.SHL on
+//     the FMA pipe; the even bits of that word are garbage, but carry-save adders are bitwise,
+//     so garbage never reaches the odd bits the masks select;
+//   * the tail vector (samples >= N masked off) and ragged batch ends run in a separate,
+//     predicated copy of the batch code, so the steady-state loop carries no predicates.
 // SPLIT warps of a CTA share one group when there are fewer groups than resident warps.
 
 __device__ __forceinline__ void csa(uint32_t &sum, uint32_t &carry, uint32_t a, uint32_t b, uint32_t c)
 {
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));   // majority
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));     // parity
+    uint32_t s, m;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(m) : "r"(a), "r"(b), "r"(c));   // majority
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(c));   // parity
+    sum = s; carry = m;
 }
 
+// ones/twos/fours/eights accumulators; add() folds 16 words (clobbered) into them and returns the
+// weight-16 carry word
 struct Tree16 {
-    uint32_t ones = 0, twos = 0, fours = 0, eights = 0;
-    // adds 16 words, returns the weight-16 carry word
-    __device__ __forceinline__ uint32_t add(const uint32_t (&w)[16])
+    uint32_t acc[4] = {0, 0, 0, 0};
+    __device__ __forceinline__ uint32_t add(uint32_t (&w)[16])
     {
-        uint32_t t[8], f[4], e[2], s;
 #pragma unroll
-        for (int i = 0; i < 8; i++) csa(ones, t[i], ones, w[2 * i], w[2 * i + 1]);
+        for (int l = 0; l < 4; l++) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) csa(twos, f[i], twos, t[2 * i], t[2 * i + 1]);
-#pragma unroll
-        for (int i = 0; i < 2; i++) csa(fours, e[i], fours, f[2 * i], f[2 * i + 1]);
-        csa(eights, s, eights, e[0], e[1]);
-        return s;
+            for (int i = 0; i < (8 >> l); i++) csa(acc[l], w[i], acc[l], w[2 * i], w[2 * i + 1]);
+        }
+        return w[0];
     }
-    // weighted popcount of the residual state under a mask
+};
+
+struct PlaneCounts {
+    Tree16 tree;
+    uint32_t sixteens = 0;
+    // two weight-16 carries -> one weight-32 carry
+    __device__ __forceinline__ uint32_t pair(uint32_t a, uint32_t b)
+    {
+        uint32_t c;
+        csa(sixteens, c, sixteens, a, b);
+        return c;
+    }
     __device__ __forceinline__ uint32_t residual(uint32_t m) const
     {
-        return 8u * __popc(eights & m) + 4u * __popc(fours & m) + 2u * __popc(twos & m) + __popc(ones & m);
+        return 16u * __popc(sixteens & m) + 8u * __popc(tree.acc[3] & m) + 4u * __popc(tree.acc[2] & m) +
+               2u * __popc(tree.acc[1] & m) + __popc(tree.acc[0] & m);
     }
 };
 
@@ -158,11 +178,12 @@ counts_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_
     __shared__ uint32_t part[8][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int kGroupsPerCta = 8 / SPLIT;
+    constexpr int kStride = 32 * SPLIT;                    // vectors between two loads of a lane
     const int sub = warp % SPLIT, gslot = warp / SPLIT;
     const int64_t ngroups = (mc + 3) >> 2;
-    const int64_t nvec = (n_samples + 15) >> 4;            // 16-byte vectors holding samples
-    const int64_t nfull = nvec - 1;
-    const int tail_bytes = (int)(n_samples - 16 * nfull);  // 1..16 valid bytes in the last vector
+    const int nvec = (int)((n_samples + 15) >> 4);         // 16-byte vectors holding samples
+    const int nfull = nvec - 1;
+    const int64_t tail_bits = 8 * (n_samples - 16 * (int64_t)nfull);   // valid bits in the last vector
     const int64_t iters = (ngroups + (int64_t)gridDim.x * kGroupsPerCta - 1) / ((int64_t)gridDim.x * kGroupsPerCta);
 
     for (int64_t it = 0; it < iters; it++) {
@@ -170,36 +191,51 @@ counts_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_
         uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, both[4] = {0, 0, 0, 0};
         if (g < ngroups) {
             const uint4 *p = reinterpret_cast<const uint4 *>(panel + g * group_stride);
-            Tree16 raw, bth;
-            for (int64_t i0 = sub * 32 + lane; i0 < nvec; i0 += 128 * SPLIT) {
-                uint32_t w[16];
+            PlaneCounts raw, bth;
+            // one batch = 8 vectors = 32 words of this lane; CHECKED: ragged end + masked tail vector
+            auto batch = [&](int i0, auto checked) {
+                constexpr bool kChecked = decltype(checked)::value;
+                uint4 v[8];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int64_t i = i0 + (int64_t)q * 32 * SPLIT;
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (i < nvec) v = ldg_stream(p + i);
-                    if (i == nfull) {                       // samples >= N are never counted
-                        v.x &= word_mask(8 * (int64_t)tail_bytes, 0); v.y &= word_mask(8 * (int64_t)tail_bytes, 1);
-                        v.z &= word_mask(8 * (int64_t)tail_bytes, 2); v.w &= word_mask(8 * (int64_t)tail_bytes, 3);
+                for (int q = 0; q < 8; q++) {
+                    const int i = i0 + q * kStride;
+                    if (!kChecked || i < nvec) v[q] = ldg_stream(p + i);
+                    else v[q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (kChecked && i == nfull) {               // samples >= N are never counted
+                        v[q].x &= word_mask(tail_bits, 0); v[q].y &= word_mask(tail_bits, 1);
+                        v[q].z &= word_mask(tail_bits, 2); v[q].w &= word_mask(tail_bits, 3);
                     }
-                    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
                 }
-                const uint32_t s = raw.add(w);
+                uint32_t s16[2], b16[2];
 #pragma unroll
-                for (int q = 0; q < 16; q++) w[q] &= w[q] >> 1;
-                const uint32_t sb = bth.add(w);
+                for (int h = 0; h < 2; h++) {
+                    uint32_t w[16], b[16];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        w[4 * q] = v[4 * h + q].x; w[4 * q + 1] = v[4 * h + q].y;
+                        w[4 * q + 2] = v[4 * h + q].z; w[4 * q + 3] = v[4 * h + q].w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; q++) b[q] = w[q] & (w[q] << 1);
+                    s16[h] = raw.tree.add(w);
+                    b16[h] = bth.tree.add(b);
+                }
+                const uint32_t s = raw.pair(s16[0], s16[1]), sb = bth.pair(b16[0], b16[1]);
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     lo[r] += __popc(s & (0x01010101u << (2 * r)));
                     hi[r] += __popc(s & (0x02020202u << (2 * r)));
-                    both[r] += __popc(sb & (0x01010101u << (2 * r)));
+                    both[r] += __popc(sb & (0x02020202u << (2 * r)));
                 }
-            }
+            };
+            int i0 = sub * 32 + lane;
+            for (; i0 + 7 * kStride < nfull; i0 += 8 * kStride) batch(i0, std::false_type());
+            if (i0 < nvec) batch(i0, std::true_type());
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                lo[r] = 16u * lo[r] + raw.residual(0x01010101u << (2 * r));
-                hi[r] = 16u * hi[r] + raw.residual(0x02020202u << (2 * r));
-                both[r] = 16u * both[r] + bth.residual(0x01010101u << (2 * r));
+                lo[r] = 32u * lo[r] + raw.residual(0x01010101u << (2 * r));
+                hi[r] = 32u * hi[r] + raw.residual(0x02020202u << (2 * r));
+                both[r] = 32u * both[r] + bth.residual(0x02020202u << (2 * r));
             }
         }
 #pragma unroll

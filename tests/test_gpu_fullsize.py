@@ -38,6 +38,22 @@ def _run(n, m, mc, k2, seed, check_rows=64):
         r = check_rows
         sub_rows = np.stack([ctx.panel_get_rows(int(sel[j]) if sel is not None else j, 1)[0] for j in range(r)])
         s1, _ = ctx.find_pheno(freq[:r], x1[:r], None, rows=None if sel is None else sel[:r], mode=capi.MODE_EXACT)
+    # the same causal rows as a compact GROUP4 panel (what the CLI stages): identical counts and
+    # EXACT phenotypes bit for bit, FAST within the stated tolerance
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        if sel is None:
+            ctx.panel_synth(PANEL_SEED, 0, mc)
+        else:
+            ctx.panel_synth_rows(PANEL_SEED, sel.astype(np.int64))
+        counts4, freq4 = ctx.find_freq()
+        assert np.array_equal(counts4, counts) and np.array_equal(freq4, freq)
+        h1, h2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_EXACT)
+        assert np.array_equal(h1, e1) and (not k2 or np.array_equal(h2, e2))
+        q1, q2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+        assert np.max(np.abs(q1 - e1)) <= 1e-5 * np.max(np.abs(e1))
+        if k2:
+            assert np.max(np.abs(q2 - e2)) <= 1e-5 * np.max(np.abs(e2))
     scale1 = np.max(np.abs(e1))
     assert np.max(np.abs(f1 - e1)) <= 1e-5 * scale1
     if k2:

@@ -42,6 +42,35 @@ def test_fast_matches_exact(n, m, mc, k):
         assert np.max(np.abs(f2 - e2)) <= 1e-5 * np.max(np.abs(e2))
 
 
+@pytest.mark.parametrize("n,m,mc,k", CASES)
+def test_group4_fast_matches_exact(n, m, mc, k):
+    """The same shapes on a compact GROUP4 panel (rows 0..mc-1 of the panel, no row list), plus a
+    re-staged shorter causal set in the same panel (stale rows behind the last group must not count)."""
+    rng = np.random.default_rng(n + 7 * m + mc)
+    x1 = rng.standard_normal(mc) * np.exp(rng.standard_normal(mc))
+    x2 = rng.standard_normal(mc) if k == 2 else None
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m, capi.LAYOUT_GROUP4)
+        ctx.panel_synth(99, 0, m)
+        counts, freq = ctx.find_freq(mc=mc)
+        assert np.all(counts.sum(axis=1) == n)
+        e1, e2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_EXACT)
+        f1, f2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+        g1, g2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+    with capi.Context(n) as ctx:                               # row-major reference of the same rows
+        ctx.panel_alloc(m)
+        ctx.panel_synth(99, 0, m)
+        rc, rf = ctx.find_freq(mc=mc)
+        r1, r2 = ctx.find_pheno(rf, x1, x2, mode=capi.MODE_EXACT)
+    assert np.array_equal(counts, rc) and np.array_equal(freq, rf)
+    assert np.array_equal(e1, r1) and (k == 1 or np.array_equal(e2, r2))    # EXACT: same bits in both layouts
+    assert np.array_equal(f1, g1)                              # FAST mode is deterministic
+    assert np.max(np.abs(f1 - e1)) <= 1e-5 * np.max(np.abs(e1))
+    if k == 2:
+        assert np.array_equal(f2, g2)
+        assert np.max(np.abs(f2 - e2)) <= 1e-5 * np.max(np.abs(e2))
+
+
 def test_many_contexts_and_reuse():
     """Contexts are independent; scratch grows and is reused across calls of different sizes."""
     a, b = capi.Context(1000), capi.Context(5000)
