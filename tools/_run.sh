@@ -1,10 +1,5 @@
-set -x
-B="python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e"
-$B > gpurun_out/plain_r01g4.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01g4.csv $B > gpurun_out/ncu_l.log 2>&1
-$B > gpurun_out/plain_r01g4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'pheno_lut_g4|counts_g4' -s 6 -c 2 -f -o gpurun_out/prof_g4_config2 $B > gpurun_out/ncu_a.log 2>&1
-$B --workload config4 > gpurun_out/plain_r01g4_c4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'pheno_lut_g4|counts_g4' -s 6 -c 2 -f -o gpurun_out/prof_g4_config4 $B --workload config4 > gpurun_out/ncu_b.log 2>&1
-tail -3 gpurun_out/ncu_a.log gpurun_out/ncu_b.log gpurun_out/ncu_l.log
-ls -la gpurun_out/*.ncu-rep
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
+$T bench.py --gpus 8 --workload config4 --steps 30 --warmup 3 --no-cpu > gpurun_out/r01_g4_bench_config4_8gpu.json 2> gpurun_out/r01_g4_bench_config4_8gpu.err
+tail -c 2500 gpurun_out/r01_g4_bench_config4_8gpu.json
+$T bench.py --gpus 8 --steps 100 --warmup 5 --no-cpu > gpurun_out/r01_g4_bench_config2_8gpu.json 2> gpurun_out/r01_g4_bench_config2_8gpu.err
+tail -c 2500 gpurun_out/r01_g4_bench_config2_8gpu.json
