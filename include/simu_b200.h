@@ -184,6 +184,21 @@ SIMU_B200_API int simu_b200_apply_heritability(simu_b200_ctx *ctx, float hsq, do
                                                const double *noise, double *effect, int64_t m,
                                                double *gen_coef, double *env_coef);
 
+/* Effect-size scaling between find_freq and find_pheno (source.cc:1245-1262, :1272-1286) and on
+ * output (:1089-1094), per causal variant with het = fabs(2 f (1 - f)):
+ *   op 0: effect *= sqrt(pow(het, S))   S = s_powK[component[j]]  (--gcta-sigma: S = -1; --traitK-s-pow)
+ *   op 1: effect /= sqrt(het)           (--norm-effect on effects read from --causal-variants)
+ *   op 2: effect *= sqrt(het)           (--norm-effect when writing .causals)
+ * effect2 / s_pow2 / component may be NULL (one trait / one component).  If a variant has
+ * het < FLT_EPSILON the call returns SIMU_B200_ERROR with its index in *bad_index (the reference
+ * throws "Causal variant ... has zero frequency", :1251-1255); effects are then unspecified.
+ * Ops 1 and 2 reproduce the host's bits (sqrt and division are correctly rounded on the device);
+ * op 0 is within 2 ulp of glibc's pow. */
+SIMU_B200_API int simu_b200_scale_effects(simu_b200_ctx *ctx, int op, const double *freq, double *effect1,
+                                          double *effect2, int64_t mc, const int32_t *component,
+                                          const double *s_pow1, const double *s_pow2, int num_components,
+                                          int64_t *bad_index);
+
 /* Sorted order of apply_liability_threshold (source.cc:1032-1034):
  * index[r] = sample of rank r, ascending pheno, ties by sample index. */
 SIMU_B200_API int simu_b200_liability_order(simu_b200_ctx *ctx, const double *pheno, int64_t n,
@@ -208,6 +223,11 @@ SIMU_B200_API int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, doub
                                              const double *d_noise, const double *d_sumsq, double *d_coef);
 SIMU_B200_API int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,
                                                 int32_t *d_index);
+/* d_s_pow: [2][num_components] exponents (trait 1 then trait 2); *d_bad_index must hold
+ * UINT64_MAX on entry and receives the smallest index with het < FLT_EPSILON, if any. */
+SIMU_B200_API int simu_b200_scale_effects_dev(simu_b200_ctx *ctx, int op, const double *d_freq, double *d_effect1,
+                                              double *d_effect2, int64_t mc, const int32_t *d_component,
+                                              const double *d_s_pow, int num_components, uint64_t *d_bad_index);
 
 /* Device time in milliseconds of the last find_freq / find_pheno call on this
  * context, measured with CUDA events on the launching stream (kernels only;

@@ -61,6 +61,9 @@ def lib() -> C.CDLL:
         L.oracle_liability_labels.argtypes = [C.c_float, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_liability_labels.restype = C.c_int
+        L.oracle_scale_effects.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+        L.oracle_scale_effects.restype = C.c_long
         L.oracle_synth_rows.argtypes = [C.c_uint64, C.c_int64, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
         _LIB = L
     return _LIB
@@ -223,6 +226,19 @@ def apply_heritability(hsq: float, pheno: np.ndarray, noise: np.ndarray, effect:
     gen = lib().oracle_apply_heritability(hsq, _ptr(pheno), pheno.size, _ptr(noise), _ptr(eff),
                                           0 if eff is None else eff.size, C.byref(env))
     return pheno, eff, gen, env.value
+
+
+def scale_effects(op: int, freq, effect1, effect2=None, component=None, s_pow1=None, s_pow2=None):
+    """source.cc:1245-1262 (op 0), :1272-1286 (op 1), :1089-1094 (op 2) on copies.
+    -> (effect1, effect2, bad) with bad = -1 or the first zero-het variant."""
+    f = np.ascontiguousarray(freq, dtype=np.float64)
+    x1 = np.array(effect1, dtype=np.float64)
+    x2 = None if effect2 is None else np.array(effect2, dtype=np.float64)
+    comp = None if component is None else np.ascontiguousarray(component, dtype=np.int32)
+    sp1 = None if s_pow1 is None else np.ascontiguousarray(np.atleast_1d(s_pow1), dtype=np.float64)
+    sp2 = None if s_pow2 is None else np.ascontiguousarray(np.atleast_1d(s_pow2), dtype=np.float64)
+    bad = lib().oracle_scale_effects(op, _ptr(f), _ptr(x1), _ptr(x2), f.size, _ptr(comp), _ptr(sp1), _ptr(sp2))
+    return x1, x2, int(bad)
 
 
 def liability_order(pheno: np.ndarray) -> np.ndarray:

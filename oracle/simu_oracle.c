@@ -211,6 +211,38 @@ int oracle_liability_labels(float k, int ncas, int ncon, size_t n, const int32_t
     return 0;
 }
 
+/* ------------------------------------------------------- effect-size scaling */
+
+/* The three per-variant effect scalings main() applies around find_pheno:
+ * op 0  source.cc:1245-1262  effect *= sqrt(pow(het, S)), S = -1 under --gcta-sigma, else
+ *                            --traitK-s-pow of the variant's component;
+ * op 1  source.cc:1272-1286  effect /= sqrt(het)   (--norm-effect, effects from a file);
+ * op 2  source.cc:1089-1094  effect *= sqrt(het)   (--norm-effect, .causals output);
+ * het = fabs(2 f (1-f)) (:1250, :1277, :1092).  Returns -1, or the index of the first variant
+ * with het < FLT_EPSILON (:1251-1255, :1278-1282: the reference throws there; op 2 has no check). */
+long oracle_scale_effects(int op, const double *freq, double *effect1, double *effect2, size_t mc,
+                          const int32_t *component, const double *s_pow1, const double *s_pow2)
+{
+    size_t j;
+    for (j = 0; j < mc; j++) {
+        const double f = freq[j];
+        const double het = fabs(2 * f * (1 - f));
+        const int c = component ? component[j] : 0;
+        if (op != 2 && het < FLT_EPSILON) return (long)j;
+        if (op == 0) {
+            effect1[j] *= sqrt(pow(het, s_pow1[c]));             /* :1258 */
+            if (effect2) effect2[j] *= sqrt(pow(het, s_pow2[c])); /* :1261 */
+        } else if (op == 1) {
+            effect1[j] /= sqrt(het);                             /* :1284 */
+            if (effect2) effect2[j] /= sqrt(het);                /* :1285 */
+        } else {
+            effect1[j] *= sqrt(het);                             /* :1093 */
+            if (effect2) effect2[j] *= sqrt(het);
+        }
+    }
+    return -1;
+}
+
 /* ------------------------------------------------------ synthetic panel gen */
 
 /* splitmix64 finaliser */

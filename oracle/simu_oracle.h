@@ -91,6 +91,11 @@ int oracle_liability_labels(float k, int ncas, int ncon, size_t n, const int32_t
 /* max_ncas / max_ncon split.  src/source.cc:1037-1039. */
 void oracle_liability_split(float k, size_t n, int *max_ncas, int *max_ncon);
 
+/* Effect-size scaling by het^S / sqrt(het).  src/source.cc:1245-1262 (op 0), :1272-1286 (op 1),
+ * :1089-1094 (op 2).  Returns -1 or the first variant whose het < FLT_EPSILON (ops 0, 1). */
+long oracle_scale_effects(int op, const double *freq, double *effect1, double *effect2, size_t mc,
+                          const int32_t *component, const double *s_pow1, const double *s_pow2);
+
 /* ---- synthetic panel generator; integer-only so that the
  * CUDA generator in simu_b200/csrc/synth.cu produces identical bytes. ---- */
 void oracle_synth_rows(uint64_t panel_seed, int64_t first_row, size_t n_rows,

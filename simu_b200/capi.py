@@ -50,6 +50,8 @@ SIGNATURES = {
     "simu_b200_apply_heritability": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp, _i64,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "simu_b200_liability_order": (_i32, [_vp, _vp, _i64, _vp]),
+    "simu_b200_scale_effects": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, C.POINTER(C.c_int64)]),
+    "simu_b200_scale_effects_dev": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "simu_b200_find_freq_dev": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "simu_b200_find_pheno_dev": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
     "simu_b200_sumsq_dev": (_i32, [_vp, _vp, _i64, _vp]),
@@ -241,6 +243,23 @@ class Context:
         self._check(self.lib.simu_b200_apply_heritability(self.h, hsq, _np_ptr(y), y.size, _np_ptr(e), _np_ptr(x),
                                                           0 if x is None else x.size, C.byref(g), C.byref(v)))
         return y, x, g.value, v.value
+
+    def scale_effects(self, op: int, freq, effect1, effect2=None, component=None, s_pow1=None, s_pow2=None):
+        """op 0: *= sqrt(pow(het, S)); 1: /= sqrt(het); 2: *= sqrt(het).  source.cc:1245-1262, :1272-1286, :1089-1094.
+        -> (effect1, effect2 or None); raises SimuB200Error(ERROR) naming the first zero-het variant."""
+        f = np.ascontiguousarray(freq, dtype=np.float64)
+        x1 = np.array(effect1, dtype=np.float64)
+        x2 = None if effect2 is None else np.array(effect2, dtype=np.float64)
+        comp = None if component is None else np.ascontiguousarray(component, dtype=np.int32)
+        sp1 = None if s_pow1 is None else np.ascontiguousarray(np.atleast_1d(s_pow1), dtype=np.float64)
+        sp2 = None if s_pow2 is None else np.ascontiguousarray(np.atleast_1d(s_pow2), dtype=np.float64)
+        ncomp = max(1, 0 if sp1 is None else sp1.size)
+        bad = C.c_int64(-1)
+        rc = self.lib.simu_b200_scale_effects(self.h, op, _np_ptr(f), _np_ptr(x1), _np_ptr(x2), f.size, _np_ptr(comp),
+                                              _np_ptr(sp1), _np_ptr(sp2), ncomp, C.byref(bad))
+        self.last_bad_index = bad.value
+        self._check(rc)
+        return x1, x2
 
     def liability_order(self, pheno) -> np.ndarray:
         y = np.ascontiguousarray(pheno, dtype=np.float64)

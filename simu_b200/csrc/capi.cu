@@ -712,6 +712,66 @@ int simu_b200_apply_heritability(simu_b200_ctx *ctx, float hsq, double *pheno, i
     return SIMU_B200_OK;
 }
 
+int simu_b200_scale_effects(simu_b200_ctx *ctx, int op, const double *freq, double *effect1, double *effect2, int64_t mc,
+                            const int32_t *component, const double *s_pow1, const double *s_pow2, int num_components,
+                            int64_t *bad_index)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (bad_index) *bad_index = -1;
+    if (op < 0 || op > 2 || mc < 0 || (mc > 0 && (!freq || !effect1)) || num_components < 1 ||
+        (op == 0 && (!s_pow1 || (effect2 && !s_pow2))))
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "scale_effects: bad arguments");
+    if (mc == 0) return SIMU_B200_OK;
+    if (component)
+        for (int64_t j = 0; j < mc; j++)
+            if (component[j] < 0 || component[j] >= num_components)
+                return ctx_fail(ctx, SIMU_B200_EINVAL, "scale_effects: component[%lld] = %d out of range", (long long)j, component[j]);
+    void *d_freq = nullptr, *d_x1 = nullptr, *d_x2 = nullptr, *d_comp = nullptr;
+    int rc;
+    if ((rc = h2d(ctx, SCR_FREQ, freq, (size_t)mc * 8, &d_freq))) return rc;
+    if ((rc = h2d(ctx, SCR_X1, effect1, (size_t)mc * 8, &d_x1))) return rc;
+    if (effect2 && (rc = h2d(ctx, SCR_X2, effect2, (size_t)mc * 8, &d_x2))) return rc;
+    if (component && (rc = h2d(ctx, SCR_ROWS, component, (size_t)mc * 4, &d_comp))) return rc;
+    // [2][ncomp] exponents followed by the "first bad variant" word
+    std::vector<double> sp(2 * (size_t)num_components + 1, 0.0);
+    for (int c = 0; c < num_components; c++) {
+        if (s_pow1) sp[c] = s_pow1[c];
+        if (s_pow2) sp[num_components + c] = s_pow2[c];
+    }
+    const unsigned long long none = ~0ull;
+    memcpy(&sp[2 * (size_t)num_components], &none, 8);
+    double *d_misc = (double *)ctx_scratch(ctx, SCR_MISC, sp.size() * 8);
+    if (!d_misc) return SIMU_B200_ENOMEM;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_misc, sp.data(), sp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long *d_bad = (unsigned long long *)(d_misc + 2 * (size_t)num_components);
+    if ((rc = launch_scale_effects(ctx, (const double *)d_freq, (double *)d_x1, (double *)d_x2, mc, (const int32_t *)d_comp,
+                                   d_misc, num_components, op, d_bad)))
+        return rc;
+    unsigned long long bad = none;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(effect1, d_x1, (size_t)mc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (effect2) CUDA_TRY(ctx, cudaMemcpyAsync(effect2, d_x2, (size_t)mc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bad != none) {
+        if (bad_index) *bad_index = (int64_t)bad;
+        return ctx_fail(ctx, SIMU_B200_ERROR, "scale_effects: causal variant %llu has zero frequency", bad);
+    }
+    return SIMU_B200_OK;
+}
+
+int simu_b200_scale_effects_dev(simu_b200_ctx *ctx, int op, const double *d_freq, double *d_effect1, double *d_effect2,
+                                int64_t mc, const int32_t *d_component, const double *d_s_pow, int num_components,
+                                uint64_t *d_bad_index)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (op < 0 || op > 2 || mc < 0 || !d_freq || !d_effect1 || !d_bad_index || num_components < 1 || (op == 0 && !d_s_pow))
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "scale_effects_dev: bad arguments");
+    return launch_scale_effects(ctx, d_freq, d_effect1, d_effect2, mc, d_component, d_s_pow, num_components, op,
+                                (unsigned long long *)d_bad_index);
+}
+
 int simu_b200_liability_order(simu_b200_ctx *ctx, const double *pheno, int64_t n, int32_t *index)
 {
     if (!ctx) return SIMU_B200_EINVAL;

@@ -93,6 +93,9 @@ int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out
 int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
                         const double *d_sumsq, double *d_coef);
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index);
+// effect-size scaling by het^S / sqrt(het).  d_spow: [2][ncomp]; *d_bad: first variant with zero het
+int launch_scale_effects(simu_b200_ctx *ctx, const double *d_freq, double *d_x1, double *d_x2, int64_t mc,
+                         const int32_t *d_comp, const double *d_spow, int ncomp, int op, unsigned long long *d_bad);
 
 // staging: move n_rows packed rows (pitch src_pitch) from a device bounce buffer into panel rows
 // [dst_row, dst_row + n_rows) -- re-pitched (ROWS) or sample-interleaved (GROUP4).  stage.cu

@@ -85,6 +85,38 @@ heritability_kernel(float hsq, double *__restrict__ y, int64_t n, const double *
         y[i] = __dadd_rn(__dmul_rn(y[i], gen_coef), __dmul_rn(noise[i], env_coef));
 }
 
+// ------------------------------------------------------- effect-size scaling
+
+// Per causal variant (source.cc:1245-1262, :1272-1286, :1089-1094):
+//   het = fabs(2 f (1 - f));   het < FLT_EPSILON -> *bad = min(index)   (the host throws)
+//   op 0:  x *= sqrt(pow(het, S_k[component]))      --gcta-sigma (S = -1) / --traitK-s-pow
+//   op 1:  x /= sqrt(het)                            --norm-effect on effects read from a file
+//   op 2:  x *= sqrt(het)                            --norm-effect on output (.causals)
+// sqrt and the division are correctly rounded on the device, so ops 1 and 2 give the host's
+// bits; pow() is within 2 ulp of glibc's (op 0 is tolerance-matched, 1e-14).
+__global__ void __launch_bounds__(256)
+scale_effects_kernel(const double *__restrict__ freq, double *__restrict__ x1, double *__restrict__ x2, int64_t mc,
+                     const int32_t *__restrict__ comp, const double *__restrict__ spow, int ncomp, int op,
+                     unsigned long long *__restrict__ bad)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= mc) return;
+    const double f = freq[j];
+    const double het = fabs(__dmul_rn(__dmul_rn(2.0, f), __dsub_rn(1.0, f)));      // :1250
+    if (op != 2 && het < (double)FLT_EPSILON) { atomicMin(bad, (unsigned long long)j); return; }   // :1251, :1278; none at :1092
+    const int c = comp ? comp[j] : 0;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        double *x = k == 0 ? x1 : x2;
+        if (!x) continue;
+        double v = x[j];
+        if (op == 0) v = __dmul_rn(v, sqrt(pow(het, spow[k * ncomp + c])));
+        else if (op == 1) v = __ddiv_rn(v, sqrt(het));
+        else v = __dmul_rn(v, sqrt(het));
+        x[j] = v;
+    }
+}
+
 // ---------------------------------------------------------------- argsort
 
 constexpr int kSortTile = 1024;     // elements per warp
@@ -324,6 +356,16 @@ int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, c
     heritability_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(hsq, d_y, n, d_noise, d_sumsq, d_coef);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "heritability launch");
+}
+
+int launch_scale_effects(simu_b200_ctx *ctx, const double *d_freq, double *d_x1, double *d_x2, int64_t mc,
+                         const int32_t *d_comp, const double *d_spow, int ncomp, int op, unsigned long long *d_bad)
+{
+    if (mc <= 0) return SIMU_B200_OK;
+    scale_effects_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, d_comp, d_spow, ncomp,
+                                                                              op, d_bad);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "scale_effects_kernel launch");
 }
 
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index)

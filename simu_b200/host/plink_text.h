@@ -16,11 +16,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
-#include <map>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <string_view>
+#include <unordered_map>
 #include <vector>
+
+#include "fastio.h"
 
 namespace simu {
 
@@ -51,39 +54,27 @@ inline std::vector<std::string> split_blank(const std::string &line)
     return out;
 }
 
-inline bool full_long(const std::string &s, long long *v)
-{
-    char *end = nullptr;
-    *v = strtoll(s.c_str(), &end, 10);
-    return !s.empty() && end && *end == '\0';
-}
-
-inline bool full_double(const std::string &s, double *v)
-{
-    char *end = nullptr;
-    *v = strtod(s.c_str(), &end);
-    return !s.empty() && end && *end == '\0';
-}
-
 inline bool parse_bim_file(const std::string &path, std::vector<Locus> *loci)
 {
-    std::ifstream f(path);
-    if (!f) return false;
-    std::string line;
-    while (std::getline(f, line)) {
-        std::vector<std::string> t = split_blank(line);
-        if (t.empty()) continue;
-        if (t.size() > 6) return false;
+    FileText f(path);                      // whole file in memory, fields tokenised in place
+    if (!f.ok()) return false;
+    char *b, *e;
+    std::string_view t[6];
+    loci->reserve(loci->size() + f.count_lines());
+    while (f.next_line(&b, &e)) {
+        const int n = FileText::split(b, e, t, 6);
+        if (n == 0) continue;
+        if (n > 6) return false;
         Locus l;
         long long v;
         double d;
         // rows with fewer than six fields are kept with defaults, as libplinkio's new_row does
-        if (t.size() > 0) { if (!full_long(t[0], &v)) return false; l.chromosome = (unsigned char)v; }
-        if (t.size() > 1) l.name = t[1];
-        if (t.size() > 2) { if (!full_double(t[2], &d)) return false; l.position = (float)d; }
-        if (t.size() > 3) { if (!full_long(t[3], &v)) return false; l.bp_position = v; }
-        if (t.size() > 4) l.allele1 = t[4];
-        if (t.size() > 5) l.allele2 = t[5];
+        if (n > 0) { if (!full_long(t[0], &v)) return false; l.chromosome = (unsigned char)v; }
+        if (n > 1) l.name.assign(t[1]);
+        if (n > 2) { if (!full_double(t[2], &d)) return false; l.position = (float)d; }
+        if (n > 3) { if (!full_long(t[3], &v)) return false; l.bp_position = v; }
+        if (n > 4) l.allele1.assign(t[4]);
+        if (n > 5) l.allele2.assign(t[5]);
         loci->push_back(std::move(l));
     }
     return true;
@@ -91,24 +82,26 @@ inline bool parse_bim_file(const std::string &path, std::vector<Locus> *loci)
 
 inline bool parse_fam_file(const std::string &path, std::vector<Sample> *samples)
 {
-    std::ifstream f(path);
-    if (!f) return false;
-    std::string line;
-    while (std::getline(f, line)) {
-        std::vector<std::string> t = split_blank(line);
-        if (t.empty()) continue;
-        if (t.size() > 6) return false;
-        if (t.size() > 4 && t[4].size() != 1) return false;                 // parse_sex
-        if (t.size() > 5) {                                                  // parse_phenotype
+    FileText f(path);
+    if (!f.ok()) return false;
+    char *b, *e;
+    std::string_view t[6];
+    samples->reserve(samples->size() + f.count_lines());
+    while (f.next_line(&b, &e)) {
+        const int n = FileText::split(b, e, t, 6);
+        if (n == 0) continue;
+        if (n > 6) return false;
+        if (n > 4 && t[4].size() != 1) return false;                        // parse_sex
+        if (n > 5) {                                                         // parse_phenotype
             double d;
-            const std::string &p = t[5];
+            const std::string_view p = t[5];
             const bool code = p.size() == 1 && (p[0] == '0' || p[0] == '1' || p[0] == '2');
-            const bool miss = strncmp(p.c_str(), "-9", p.size()) == 0;
+            const bool miss = strncmp(std::string(p).c_str(), "-9", p.size()) == 0;
             if (!code && !miss && !full_double(p, &d)) return false;
         }
         Sample s;
-        s.fid = t[0];
-        if (t.size() > 1) s.iid = t[1];
+        s.fid.assign(t[0]);
+        if (n > 1) s.iid.assign(t[1]);
         samples->push_back(std::move(s));
     }
     return true;
@@ -169,15 +162,18 @@ public:
     {
         if (!snp_to_id_.empty())
             throw std::runtime_error("internal error - find_variant_index_map must be called once");
-        for (int v = 0; v < num_variants_; v++) {
-            const Locus *l = get_locus(v);
-            if (!snp_to_id_.insert({l->name, v}).second)
-                throw std::runtime_error("ERROR: duplicated variant name: " + l->name);
-        }
+        // hash map keyed by views of the loci's own names (the loci never move once all files are
+        // pushed); the reference's std::map costs O(log M) string compares per insert and lookup
+        snp_to_id_.reserve((size_t)num_variants_ * 2);
+        int v = 0;
+        for (const PlinkFile &f : files_)
+            for (const Locus &l : f.loci)
+                if (!snp_to_id_.emplace(std::string_view(l.name), v++).second)
+                    throw std::runtime_error("ERROR: duplicated variant name: " + l.name);
     }
     int get_locus_id(const std::string &name) const                                // source.cc:345-352
     {
-        auto it = snp_to_id_.find(name);
+        auto it = snp_to_id_.find(std::string_view(name));
         if (it == snp_to_id_.end())
             throw std::runtime_error("ERROR: locus with name " + name +
                                      " does not exist in the input; check your --bfile and/or --causal-variants, "
@@ -188,7 +184,7 @@ public:
 private:
     std::vector<PlinkFile> files_;
     std::vector<int> offsets_;
-    std::map<std::string, int> snp_to_id_;
+    std::unordered_map<std::string_view, int> snp_to_id_;
     int num_variants_ = 0;
 };
 

@@ -21,6 +21,7 @@
 #include <sys/stat.h>
 
 #include "../../include/simu_b200.h"
+#include "fastio.h"
 #include "options.h"
 #include "plink_text.h"
 #include "rng.h"
@@ -572,7 +573,7 @@ void draw_effect_sizes(const SimuOptions &o, Mt19937 &rng, const std::vector<int
 
 void save_pheno_file(const SimuOptions &o, const PlinkFiles &pio, const std::vector<double> &p1, const std::vector<double> &p2)
 {
-    std::ofstream file(o.out_pheno);
+    TextWriter file(o.out_pheno);          // same characters as the reference's ofstream << (fastio.h)
     const bool bivariate = o.num_traits == 2;
     file << "FID\tIID\ttrait1" << (bivariate ? "\ttrait2" : "") << "\n";
     for (size_t i = 0; i < p1.size(); i++) {
@@ -586,7 +587,7 @@ void save_pheno_file(const SimuOptions &o, const PlinkFiles &pio, const std::vec
 void save_causals_file(const SimuOptions &o, const std::string &path, const PlinkFiles &pio, const std::vector<double> &freq,
                        const std::vector<int> &comp, const std::vector<double> &effect_per_variant)
 {
-    std::ofstream file(path);
+    TextWriter file(path);
     file << "SNP\tCHR\tPOS\tA1\tA2\tFRQ";
     for (int i = 0; i < o.num_components; i++) file << "\tBETA_c" << (i + 1);
     file << "\n";

@@ -303,6 +303,35 @@ def test_apply_heritability_parity():
         assert (gen, env) == (0.0, 1.0) and np.array_equal(gy, noise)
 
 
+def test_scale_effects_parity():
+    """het^S / sqrt(het) effect scaling (source.cc:1245-1262, :1272-1286, :1089-1094) on the device:
+    sqrt and division are correctly rounded -> ops 1, 2 bit-exact; pow -> 1e-14."""
+    rng = np.random.default_rng(12)
+    mc = 20_011
+    freq = rng.uniform(0.001, 0.999, mc)
+    x1, x2 = rng.standard_normal(mc), rng.standard_normal(mc)
+    comp = rng.integers(0, 3, mc).astype(np.int32)
+    sp1, sp2 = np.array([-1.0, -0.25, 0.5]), np.array([-1.0, 0.0, 1.0])
+    with capi.Context(16) as ctx:
+        for op in (1, 2):
+            g1, g2 = ctx.scale_effects(op, freq, x1, x2)
+            o1, o2, bad = oracle.scale_effects(op, freq, x1, x2)
+            assert bad == -1 and np.array_equal(g1, o1) and np.array_equal(g2, o2)
+        g1, g2 = ctx.scale_effects(0, freq, x1, x2, comp, sp1, sp2)
+        o1, o2, bad = oracle.scale_effects(0, freq, x1, x2, comp, sp1, sp2)
+        assert np.max(np.abs(g1 - o1) / np.abs(o1)) <= 1e-14 and np.max(np.abs(g2 - o2) / np.abs(o2)) <= 1e-14
+        g1, _ = ctx.scale_effects(0, freq, x1, None, None, [-1.0])              # --gcta-sigma, one trait
+        o1, _, _ = oracle.scale_effects(0, freq, x1, None, None, [-1.0])
+        assert np.max(np.abs(g1 - o1) / np.abs(o1)) <= 1e-14
+        # a monomorphic causal variant: the reference throws (source.cc:1251-1255)
+        f0 = freq.copy(); f0[[777, 5000]] = [0.0, 1.0]
+        with pytest.raises(capi.SimuB200Error) as ei:
+            ctx.scale_effects(0, f0, x1, x2, comp, sp1, sp2)
+        assert ei.value.status == capi.ERROR and ctx.last_bad_index == 777
+        assert oracle.scale_effects(0, f0, x1, x2, comp, sp1, sp2)[2] == 777
+        assert ctx.scale_effects(1, freq[:0], x1[:0])[0].size == 0
+
+
 @pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 1000, 1024, 1025, 100000])
 def test_liability_order_bit_exact(n):
     rng = np.random.default_rng(n)

@@ -193,3 +193,20 @@ def test_synth_rows_statistics():
     # deterministic and row-addressable
     again = oracle.synth_rows(20240901, 7, 3, n)
     assert np.array_equal(again, rows[7:10])
+
+
+def test_scale_effects_restatement():
+    """oracle.scale_effects against the formulas of source.cc:1250-1262, :1277-1285, :1092-1093."""
+    rng = np.random.default_rng(3)
+    f = rng.uniform(0.01, 0.99, 500)
+    x1, x2 = rng.standard_normal(500), rng.standard_normal(500)
+    het = np.abs(2 * f * (1 - f))
+    o1, o2, bad = oracle.scale_effects(0, f, x1, x2, None, [-1.0], [0.5])
+    assert bad == -1
+    assert np.allclose(o1, x1 * np.sqrt(het ** -1.0), rtol=1e-15) and np.allclose(o2, x2 * np.sqrt(het ** 0.5), rtol=1e-15)
+    o1, _, _ = oracle.scale_effects(1, f, x1)
+    assert np.array_equal(o1, x1 / np.sqrt(het))
+    o1, _, _ = oracle.scale_effects(2, f, x1)
+    assert np.array_equal(o1, x1 * np.sqrt(het))
+    f[7] = 0.0
+    assert oracle.scale_effects(1, f, x1)[2] == 7 and oracle.scale_effects(2, f, x1)[2] == -1
