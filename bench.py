@@ -76,15 +76,19 @@ def _causal_rows(w, rank):
     return np.sort(rng.choice(w["m"], w["mc"], replace=False)).astype(np.int32)
 
 
-def _effects(w, freq, rank):
-    """Bivariate normal effects (source.cc:940-948) with --gcta-sigma scaling (:1257-1262)."""
+def _raw_effects(w, rank):
+    """Bivariate normal effect draws (source.cc:940-948), before the --gcta-sigma scaling."""
     rng = np.random.default_rng(1000 + rank)
     z1, z2 = rng.standard_normal(w["mc"]), rng.standard_normal(w["mc"])
+    return z1, ((RG * z1 + np.sqrt(1.0 - RG * RG) * z2) if w["k"] == 2 else None)
+
+
+def _effects(w, freq, rank):
+    """... with --gcta-sigma scaling (:1257-1262)."""
+    r1, r2 = _raw_effects(w, rank)
     het = np.abs(2.0 * freq * (1.0 - freq))
     scale = np.sqrt(np.power(np.maximum(het, 1e-12), -1.0))
-    x1 = z1 * scale
-    x2 = (RG * z1 + np.sqrt(1.0 - RG * RG) * z2) * scale
-    return x1, (x2 if w["k"] == 2 else None)
+    return r1 * scale, (r2 * scale if w["k"] == 2 else None)
 
 
 def alg_bytes(w):
@@ -288,11 +292,27 @@ def run_ours(args, w):
     d_misc = torch.zeros(8, dtype=torch.float64, device=dev)
     d_index = torch.empty(n, dtype=torch.int32, device=dev)
     mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
+    fused = args.fused and g4 and mode == capi.MODE_FAST
+    if fused:      # one pass: the raw draws go in, the kernel scales them by het^-1/2 (--gcta-sigma) itself
+        r1, r2 = _raw_effects(w, rank)
+        fused_op = 0
+        if os.environ.get("SIMU_B200_FUSED_PREBUILT"):      # A/B: same schedule, tables prebuilt from a counts pass
+            r1, r2, fused_op = x1, x2, -1
+        d_r1 = torch.from_numpy(r1).to(dev)
+        d_r2 = torch.from_numpy(r2).to(dev) if k == 2 else None
+        d_spow = torch.tensor([-1.0, -1.0], dtype=torch.float64, device=dev)
+        d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
 
     def step():
-        ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
-        ctx.find_pheno_dev(rows_ptr, mc, d_freq.data_ptr(), d_x1.data_ptr(), d_x2.data_ptr() if k == 2 else 0,
-                           d_y[0].data_ptr(), d_y[1].data_ptr() if k == 2 else 0, mode)
+        if fused:
+            ctx.find_freq_pheno_dev(mc, d_r1.data_ptr(), d_r2.data_ptr() if k == 2 else 0, fused_op, 0, d_spow.data_ptr(), 1,
+                                    d_counts.data_ptr(), d_freq.data_ptr(), d_x1.data_ptr(),
+                                    d_x2.data_ptr() if k == 2 else 0, d_y[0].data_ptr(),
+                                    d_y[1].data_ptr() if k == 2 else 0, d_bad.data_ptr())
+        else:
+            ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
+            ctx.find_pheno_dev(rows_ptr, mc, d_freq.data_ptr(), d_x1.data_ptr(), d_x2.data_ptr() if k == 2 else 0,
+                               d_y[0].data_ptr(), d_y[1].data_ptr() if k == 2 else 0, mode)
         if world > 1:
             dist.all_reduce(d_y)                     # the path's one exchange step
         for t in range(k):
@@ -325,7 +345,7 @@ def run_ours(args, w):
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
     prof = {name: ctx.profile_read(i) for name, i in (("counts", 0), ("pheno_exact", 1), ("lut_main", 2),
-                                                     ("lut_build", 3), ("lut_reduce", 4))}
+                                                     ("lut_build", 3), ("lut_reduce", 4), ("fused", 7))}
     ctx.profile_enable(False)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -501,6 +521,8 @@ def main():
     ap.add_argument("--layout", default="group4", choices=["group4", "rows"],
                     help="HBM panel: compact causal rows in GROUP4 layout (what the CLI stages) or the whole "
                          ".bed slice row-major with a causal row list")
+    ap.add_argument("--fused", action="store_true",
+                    help="one pass over HBM: simu_b200_find_freq_pheno (counts + effect scaling + lookups in one kernel)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()

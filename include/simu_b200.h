@@ -177,6 +177,26 @@ SIMU_B200_API int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, 
                                        const double *freq, const double *effect1, const double *effect2,
                                        double *pheno1, double *pheno2, int mode);
 
+/* find_freq + effect scaling + find_pheno (FAST mode) in ONE pass over the panel: the fused
+ * kernel counts a row block a few steps before it looks it up, so HBM is read once instead of
+ * twice.  GROUP4 panels only; rows 0..mc-1.  It replaces this stretch of main():
+ *     find_freq(...)                                   source.cc:1235
+ *     draw / read effect sizes, scale them by het      source.cc:1238-1290
+ *     find_pheno(...)                                  source.cc:1295
+ * raw1/raw2: the effect sizes BEFORE the het scaling (the RNG draws of :887-949, or the file's
+ * values) -- the draws do not depend on the frequencies, so the host makes them first, in the
+ * reference's RNG order.  scale_op: -1 none; 0: *= sqrt(pow(het, S)) (--gcta-sigma S = -1,
+ * --traitK-s-pow); 1: /= sqrt(het) (--norm-effect with --causal-variants effects), as in
+ * simu_b200_scale_effects.  Outputs: counts / freq (as find_freq), effect1/effect2 = the SCALED
+ * effects (what .causals reports after apply_heritability), pheno1/pheno2.  Any output except
+ * pheno may be NULL.  Returns SIMU_B200_ERROR with *bad_index set when a causal variant has
+ * het < FLT_EPSILON under scale_op 0/1 (the reference throws, :1251-1255). */
+SIMU_B200_API int simu_b200_find_freq_pheno(simu_b200_ctx *ctx, int64_t mc, const double *raw1, const double *raw2,
+                                            int scale_op, const int32_t *component, const double *s_pow1,
+                                            const double *s_pow2, int num_components, int32_t *counts,
+                                            double *freq, double *effect1, double *effect2, double *pheno1,
+                                            double *pheno2, int64_t *bad_index);
+
 /* apply_heritability (source.cc:1008-1029) with the N noise draws made by the
  * caller's RNG.  pheno updated in place; effect (m entries, may be NULL)
  * scaled by gen_coef on the host side of the call. */
@@ -215,6 +235,12 @@ SIMU_B200_API int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_
                                            const double *d_freq, const double *d_effect1,
                                            const double *d_effect2, double *d_pheno1, double *d_pheno2,
                                            int mode);
+/* d_s_pow: [2][num_components]; *d_bad_index (device) is set to UINT64_MAX or the first zero-het variant. */
+SIMU_B200_API int simu_b200_find_freq_pheno_dev(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1,
+                                                const double *d_raw2, int scale_op, const int32_t *d_component,
+                                                const double *d_s_pow, int num_components, int32_t *d_counts,
+                                                double *d_freq, double *d_effect1, double *d_effect2,
+                                                double *d_pheno1, double *d_pheno2, uint64_t *d_bad_index);
 /* *d_out = sum(y[i]^2)  (source.cc:1011). */
 SIMU_B200_API int simu_b200_sumsq_dev(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out);
 /* gen/env from *d_sumsq exactly as source.cc:1012-1025, written to
@@ -237,7 +263,8 @@ SIMU_B200_API int simu_b200_last_kernel_ms(simu_b200_ctx *ctx, int which, float 
 /* Per-kernel device timing for bench.py's roofline: when enabled, every launch of the hot
  * kernels is bracketed by a CUDA event pair on the launching stream (up to 512 pairs, then
  * recording stops).  kernel_id: 0 = allele counts, 1 = find_pheno EXACT, 2 = find_pheno FAST
- * main (LUT) kernel, 3 = LUT build, 4 = LUT slot reduce, 5 = sumsq/heritability, 6 = sort.
+ * main (LUT) kernel, 3 = LUT build, 4 = LUT slot reduce, 5 = sumsq/heritability, 6 = sort,
+ * 7 = fused one-pass kernel.
  * profile_read synchronises the stream and returns the summed milliseconds and the number
  * of recorded launches; profile_enable resets the record. */
 SIMU_B200_API int simu_b200_profile_enable(simu_b200_ctx *ctx, int on);

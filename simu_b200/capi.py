@@ -47,6 +47,9 @@ SIGNATURES = {
     "simu_b200_panel_get_rows": (_i32, [_vp, _i64, _i64, _vp, _i64]),
     "simu_b200_find_freq": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "simu_b200_find_pheno": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "simu_b200_find_freq_pheno": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         C.POINTER(C.c_int64)]),
+    "simu_b200_find_freq_pheno_dev": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "simu_b200_apply_heritability": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp, _i64,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "simu_b200_liability_order": (_i32, [_vp, _vp, _i64, _vp]),
@@ -232,6 +235,30 @@ class Context:
                                                   _np_ptr(y1), _np_ptr(y2), mode))
         return y1, y2
 
+    def find_freq_pheno(self, raw1, raw2=None, scale_op: int = -1, component=None, s_pow1=None, s_pow2=None, mc=None):
+        """find_freq + effect scaling + find_pheno (FAST) in one pass (GROUP4 panels).
+        -> (counts, freq, effect1, effect2 or None, pheno1, pheno2 or None)."""
+        r1 = np.ascontiguousarray(raw1, dtype=np.float64)
+        r2 = None if raw2 is None else np.ascontiguousarray(raw2, dtype=np.float64)
+        mc = r1.size if mc is None else mc
+        comp = None if component is None else np.ascontiguousarray(component, dtype=np.int32)
+        sp1 = None if s_pow1 is None else np.ascontiguousarray(np.atleast_1d(s_pow1), dtype=np.float64)
+        sp2 = None if s_pow2 is None else np.ascontiguousarray(np.atleast_1d(s_pow2), dtype=np.float64)
+        ncomp = max(1, 0 if sp1 is None else sp1.size)
+        counts = np.zeros((mc, 4), dtype=np.int32)
+        freq = np.zeros(mc, dtype=np.float64)
+        x1 = np.zeros(mc, dtype=np.float64)
+        x2 = None if r2 is None else np.zeros(mc, dtype=np.float64)
+        y1 = np.zeros(self.num_samples, dtype=np.float64)
+        y2 = None if r2 is None else np.zeros(self.num_samples, dtype=np.float64)
+        bad = C.c_int64(-1)
+        rc = self.lib.simu_b200_find_freq_pheno(self.h, mc, _np_ptr(r1), _np_ptr(r2), scale_op, _np_ptr(comp), _np_ptr(sp1),
+                                                _np_ptr(sp2), ncomp, _np_ptr(counts), _np_ptr(freq), _np_ptr(x1), _np_ptr(x2),
+                                                _np_ptr(y1), _np_ptr(y2), C.byref(bad))
+        self.last_bad_index = bad.value
+        self._check(rc)
+        return counts, freq, x1, x2, y1, y2
+
     def apply_heritability(self, hsq: float, pheno, noise, effect=None):
         """-> (pheno, effect, gen_coef, env_coef).  source.cc:1008-1029."""
         y = np.array(pheno, dtype=np.float64)
@@ -276,6 +303,13 @@ class Context:
         self._check(self.lib.simu_b200_find_pheno_dev(self.h, C.c_void_p(d_rows or 0), mc, C.c_void_p(d_freq),
                                                       C.c_void_p(d_x1), C.c_void_p(d_x2 or 0), C.c_void_p(d_y1),
                                                       C.c_void_p(d_y2 or 0), mode))
+
+    def find_freq_pheno_dev(self, mc, d_raw1, d_raw2, scale_op, d_comp, d_spow, ncomp, d_counts, d_freq, d_x1, d_x2,
+                            d_y1, d_y2, d_bad):
+        v = lambda p: C.c_void_p(p or 0)
+        self._check(self.lib.simu_b200_find_freq_pheno_dev(self.h, mc, v(d_raw1), v(d_raw2), scale_op, v(d_comp), v(d_spow),
+                                                           ncomp, v(d_counts), v(d_freq), v(d_x1), v(d_x2), v(d_y1),
+                                                           v(d_y2), v(d_bad)))
 
     def sumsq_dev(self, d_y, n, d_out):
         self._check(self.lib.simu_b200_sumsq_dev(self.h, C.c_void_p(d_y), n, C.c_void_p(d_out)))

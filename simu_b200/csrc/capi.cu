@@ -147,7 +147,7 @@ void simu_b200_close(simu_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->panel) cudaFree(ctx->panel);
-    for (int i = 0; i < 12; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 16; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->dstage[i]) cudaFree(ctx->dstage[i]);
@@ -685,6 +685,99 @@ int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, co
     if (pheno2) CUDA_TRY(ctx, cudaMemcpyAsync(pheno2, d_y2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_a, ctx->ev_b));
+    return SIMU_B200_OK;
+}
+
+int simu_b200_find_freq_pheno_dev(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2,
+                                  int scale_op, const int32_t *d_component, const double *d_s_pow, int num_components,
+                                  int32_t *d_counts, double *d_freq, double *d_effect1, double *d_effect2,
+                                  double *d_pheno1, double *d_pheno2, uint64_t *d_bad_index)
+{
+    int rc = check_hot(ctx, "find_freq_pheno", mc, nullptr);
+    if (rc) return rc;
+    if (ctx->layout != SIMU_B200_LAYOUT_GROUP4)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: needs a GROUP4 panel (compact causal rows)");
+    if (mc > ctx->panel_rows)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: %lld causal rows but panel holds %lld", (long long)mc,
+                        (long long)ctx->panel_rows);
+    if (!d_raw1 || !d_pheno1 || !d_bad_index || ((d_raw2 == nullptr) != (d_pheno2 == nullptr)) || scale_op < -1 ||
+        scale_op > 1 || num_components < 1 || (scale_op == 0 && !d_s_pow))
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: bad arguments");
+    CUDA_TRY(ctx, cudaMemsetAsync(d_bad_index, 0xFF, 8, ctx->stream));
+    if (mc == 0) {
+        CUDA_TRY(ctx, cudaMemsetAsync(d_pheno1, 0, (size_t)ctx->n_samples * 8, ctx->stream));
+        if (d_pheno2) CUDA_TRY(ctx, cudaMemsetAsync(d_pheno2, 0, (size_t)ctx->n_samples * 8, ctx->stream));
+        return SIMU_B200_OK;
+    }
+    int fused = 1;
+    if (const char *e = getenv("SIMU_B200_FUSED_PREBUILT")) fused = atoi(e) ? 0 : 1;   // A/B: same schedule, two passes
+    if (!fused) {
+        if (scale_op != -1 || !d_freq)
+            return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: the two-pass A/B mode needs scale_op -1 and a freq buffer");
+        if ((rc = launch_counts(ctx, nullptr, mc, d_counts, d_freq))) return rc;
+    }
+    return launch_pheno_fused(ctx, mc, d_raw1, d_raw2, scale_op, d_component, d_s_pow, num_components, d_counts, d_freq,
+                              d_effect1, d_effect2, d_pheno1, d_pheno2, (unsigned long long *)d_bad_index, fused, d_freq);
+}
+
+int simu_b200_find_freq_pheno(simu_b200_ctx *ctx, int64_t mc, const double *raw1, const double *raw2, int scale_op,
+                              const int32_t *component, const double *s_pow1, const double *s_pow2, int num_components,
+                              int32_t *counts, double *freq, double *effect1, double *effect2, double *pheno1,
+                              double *pheno2, int64_t *bad_index)
+{
+    int rc = check_hot(ctx, "find_freq_pheno", mc, nullptr);
+    if (rc) return rc;
+    if (bad_index) *bad_index = -1;
+    if (!pheno1 || ((raw2 == nullptr) != (pheno2 == nullptr)) || (mc > 0 && !raw1) || num_components < 1 ||
+        (scale_op == 0 && (!s_pow1 || (raw2 && !s_pow2))))
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: bad arguments");
+    const int64_t n = ctx->n_samples;
+    if (mc == 0) {
+        for (int64_t i = 0; i < n; i++) { pheno1[i] = 0; if (pheno2) pheno2[i] = 0; }
+        return SIMU_B200_OK;
+    }
+    if (component)
+        for (int64_t j = 0; j < mc; j++)
+            if (component[j] < 0 || component[j] >= num_components)
+                return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: component[%lld] = %d out of range", (long long)j, component[j]);
+    void *d_r1 = nullptr, *d_r2 = nullptr, *d_comp = nullptr;
+    if ((rc = h2d(ctx, SCR_RAW1, raw1, (size_t)mc * 8, &d_r1))) return rc;
+    if (raw2 && (rc = h2d(ctx, SCR_RAW2, raw2, (size_t)mc * 8, &d_r2))) return rc;
+    if (component && (rc = h2d(ctx, SCR_ROWS, component, (size_t)mc * 4, &d_comp))) return rc;
+    std::vector<double> sp(2 * (size_t)num_components + 1, 0.0);
+    for (int c = 0; c < num_components; c++) {
+        if (s_pow1) sp[c] = s_pow1[c];
+        if (s_pow2) sp[num_components + c] = s_pow2[c];
+    }
+    double *d_sp = (double *)ctx_scratch(ctx, SCR_SPOW, sp.size() * 8);
+    int32_t *d_counts = (int32_t *)ctx_scratch(ctx, SCR_COUNTS, (size_t)mc * 16);
+    double *d_freq = (double *)ctx_scratch(ctx, SCR_FREQ, (size_t)mc * 8);
+    double *d_x1 = (double *)ctx_scratch(ctx, SCR_X1, (size_t)mc * 8);
+    double *d_x2 = raw2 ? (double *)ctx_scratch(ctx, SCR_X2, (size_t)mc * 8) : nullptr;
+    double *d_y1 = (double *)ctx_scratch(ctx, SCR_Y1, (size_t)n * 8);
+    double *d_y2 = raw2 ? (double *)ctx_scratch(ctx, SCR_Y2, (size_t)n * 8) : nullptr;
+    if (!d_sp || !d_counts || !d_freq || !d_x1 || (raw2 && !d_x2) || !d_y1 || (raw2 && !d_y2)) return SIMU_B200_ENOMEM;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_sp, sp.data(), sp.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    rc = simu_b200_find_freq_pheno_dev(ctx, mc, (const double *)d_r1, (const double *)d_r2, scale_op, (const int32_t *)d_comp,
+                                       d_sp, num_components, d_counts, d_freq, d_x1, d_x2, d_y1, d_y2,
+                                       (uint64_t *)(d_sp + 2 * (size_t)num_components));
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    unsigned long long bad = ~0ull;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&bad, d_sp + 2 * (size_t)num_components, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)mc * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (freq) CUDA_TRY(ctx, cudaMemcpyAsync(freq, d_freq, (size_t)mc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (effect1) CUDA_TRY(ctx, cudaMemcpyAsync(effect1, d_x1, (size_t)mc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (effect2 && d_x2) CUDA_TRY(ctx, cudaMemcpyAsync(effect2, d_x2, (size_t)mc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(pheno1, d_y1, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pheno2) CUDA_TRY(ctx, cudaMemcpyAsync(pheno2, d_y2, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_a, ctx->ev_b));
+    if (bad != ~0ull) {
+        if (bad_index) *bad_index = (int64_t)bad;
+        return ctx_fail(ctx, SIMU_B200_ERROR, "find_freq_pheno: causal variant %llu has zero frequency", bad);
+    }
     return SIMU_B200_OK;
 }
 

@@ -16,22 +16,15 @@
 // __reduce_add_sync.
 //
 // Algorithmic bytes per SNP: ceil(N/4) read + 16 (counts) + 8 (freq) written.
-#include <type_traits>
-
+#include "counts_g4.cuh"
 #include "ctx.cuh"
 
 namespace {
 
 constexpr uint32_t kLoMask = 0x55555555u;
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
+using g4::ldg_stream;
+using g4::word_mask;
 
 struct LaneCounts {
     uint32_t ones = 0, twos = 0;      // carry-save state of the raw words
@@ -55,14 +48,6 @@ struct LaneCounts {
         both += __popc(p1) + __popc(p2);
     }
 };
-
-__device__ __forceinline__ uint32_t word_mask(int64_t valid_bits, int w)
-{
-    int64_t b = valid_bits - 32 * w;
-    if (b <= 0) return 0u;
-    if (b >= 32) return 0xFFFFFFFFu;
-    return (1u << (int)b) - 1u;
-}
 
 __global__ void __launch_bounds__(256)
 counts_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32_t *__restrict__ rows,
@@ -115,60 +100,8 @@ counts_kernel(const uint8_t *__restrict__ panel, int64_t row_stride, const int32
 
 // ------------------------------------------------------------ GROUP4 layout
 //
-// In a GROUP4 panel a 32-bit word holds 4 samples x 4 SNP rows (row r of the group in bits
-// 8s+2r, 8s+2r+1), so ONE pass over a group yields the counts of its four SNPs: the words go
-// through the same kind of carry-save tree, only the final POPCs are taken under per-row masks.
-// LOP3 / SHF issue on the half-rate ALU pipe (64 lanes/clk/SM), which makes this kernel
-// ALU-bound long before it is HBM-bound unless the logic per word is kept near the tree's
-// inherent 2 LOP3 per word and plane:
-//   * the tree is 5 levels deep (ones .. sixteens, POPC of the weight-32 carry word), so the 12
-//     masked POPCs (4 rows x {lo, hi, lo&hi}) are paid once per 32 words = 512 genotypes;
-//   * the lo&hi plane is fed into a second tree as w & (w << 1) -- the shift is an IMAD.SHL on
-//     the FMA pipe; the even bits of that word are garbage, but carry-save adders are bitwise,
-//     so garbage never reaches the odd bits the masks select;
-//   * the tail vector (samples >= N masked off) and ragged batch ends run in a separate,
-//     predicated copy of the batch code, so the steady-state loop carries no predicates.
-// SPLIT warps of a CTA share one group when there are fewer groups than resident warps.
-
-__device__ __forceinline__ void csa(uint32_t &sum, uint32_t &carry, uint32_t a, uint32_t b, uint32_t c)
-{
-    uint32_t s, m;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(m) : "r"(a), "r"(b), "r"(c));   // majority
-    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(c));   // parity
-    sum = s; carry = m;
-}
-
-// ones/twos/fours/eights accumulators; add() folds 16 words (clobbered) into them and returns the
-// weight-16 carry word
-struct Tree16 {
-    uint32_t acc[4] = {0, 0, 0, 0};
-    __device__ __forceinline__ uint32_t add(uint32_t (&w)[16])
-    {
-#pragma unroll
-        for (int l = 0; l < 4; l++) {
-#pragma unroll
-            for (int i = 0; i < (8 >> l); i++) csa(acc[l], w[i], acc[l], w[2 * i], w[2 * i + 1]);
-        }
-        return w[0];
-    }
-};
-
-struct PlaneCounts {
-    Tree16 tree;
-    uint32_t sixteens = 0;
-    // two weight-16 carries -> one weight-32 carry
-    __device__ __forceinline__ uint32_t pair(uint32_t a, uint32_t b)
-    {
-        uint32_t c;
-        csa(sixteens, c, sixteens, a, b);
-        return c;
-    }
-    __device__ __forceinline__ uint32_t residual(uint32_t m) const
-    {
-        return 16u * __popc(sixteens & m) + 8u * __popc(tree.acc[3] & m) + 4u * __popc(tree.acc[2] & m) +
-               2u * __popc(tree.acc[1] & m) + __popc(tree.acc[0] & m);
-    }
-};
+// One warp per 4-row group (counts_g4.cuh has the carry-save counting itself); SPLIT warps of a
+// CTA share one group when there are fewer groups than resident warps.
 
 template <int SPLIT>
 __global__ void __launch_bounds__(256)
@@ -189,55 +122,9 @@ counts_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_
     for (int64_t it = 0; it < iters; it++) {
         const int64_t g = (it * gridDim.x + blockIdx.x) * kGroupsPerCta + gslot;
         uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, both[4] = {0, 0, 0, 0};
-        if (g < ngroups) {
-            const uint4 *p = reinterpret_cast<const uint4 *>(panel + g * group_stride);
-            PlaneCounts raw, bth;
-            // one batch = 8 vectors = 32 words of this lane; CHECKED: ragged end + masked tail vector
-            auto batch = [&](int i0, auto checked) {
-                constexpr bool kChecked = decltype(checked)::value;
-                uint4 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int i = i0 + q * kStride;
-                    if (!kChecked || i < nvec) v[q] = ldg_stream(p + i);
-                    else v[q] = make_uint4(0u, 0u, 0u, 0u);
-                    if (kChecked && i == nfull) {               // samples >= N are never counted
-                        v[q].x &= word_mask(tail_bits, 0); v[q].y &= word_mask(tail_bits, 1);
-                        v[q].z &= word_mask(tail_bits, 2); v[q].w &= word_mask(tail_bits, 3);
-                    }
-                }
-                uint32_t s16[2], b16[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    uint32_t w[16], b[16];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        w[4 * q] = v[4 * h + q].x; w[4 * q + 1] = v[4 * h + q].y;
-                        w[4 * q + 2] = v[4 * h + q].z; w[4 * q + 3] = v[4 * h + q].w;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 16; q++) b[q] = w[q] & (w[q] << 1);
-                    s16[h] = raw.tree.add(w);
-                    b16[h] = bth.tree.add(b);
-                }
-                const uint32_t s = raw.pair(s16[0], s16[1]), sb = bth.pair(b16[0], b16[1]);
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    lo[r] += __popc(s & (0x01010101u << (2 * r)));
-                    hi[r] += __popc(s & (0x02020202u << (2 * r)));
-                    both[r] += __popc(sb & (0x02020202u << (2 * r)));
-                }
-            };
-            int i0 = sub * 32 + lane;
-            for (; i0 + 7 * kStride < nfull; i0 += 8 * kStride) batch(i0, std::false_type());
-            if (i0 < nvec) batch(i0, std::true_type());
-#pragma unroll
-            for (int r = 0; r < 4; r++) {
-                lo[r] = 32u * lo[r] + raw.residual(0x01010101u << (2 * r));
-                hi[r] = 32u * hi[r] + raw.residual(0x02020202u << (2 * r));
-                both[r] = 32u * both[r] + bth.residual(0x02020202u << (2 * r));
-            }
-        }
+        if (g < ngroups)
+            g4::count_vectors(reinterpret_cast<const uint4 *>(panel + g * group_stride), sub * 32 + lane, kStride, nvec,
+                              nfull, tail_bits, lo, hi, both);
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             lo[r] = __reduce_add_sync(0xFFFFFFFFu, lo[r]);
