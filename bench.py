@@ -291,6 +291,8 @@ def run_ours(args, w):
     d_noise = torch.randn((k, n), dtype=torch.float64, generator=g).to(dev)   # e: same draws on every rank
     d_misc = torch.zeros(8, dtype=torch.float64, device=dev)
     d_index = torch.empty(n, dtype=torch.int32, device=dev)
+    d_is_case = torch.empty(n, dtype=torch.uint8, device=dev)
+    max_ncon = n - int(np.floor(np.float32(0.1) * np.float32(n)))        # --k 0.1 (source.cc:1038-1039)
     mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
     fused = args.fused and g4 and mode == capi.MODE_FAST
     if fused:      # one pass: the raw draws go in, the kernel scales them by het^-1/2 (--gcta-sigma) itself
@@ -319,8 +321,11 @@ def run_ours(args, w):
             ctx.sumsq_dev(d_y[t].data_ptr(), n, d_misc[t].data_ptr())
             ctx.heritability_dev(HSQ[t], d_y[t].data_ptr(), n, d_noise[t].data_ptr(), d_misc[t].data_ptr(),
                                  d_misc[4 + 2 * t].data_ptr())
-        if w["cc"]:
-            ctx.liability_order_dev(d_y[0].data_ptr(), n, d_index.data_ptr())
+        if w["cc"]:      # default --ncas/--ncon: both pools fully labelled -> the order statistic decides
+            if args.cc_sort:
+                ctx.liability_order_dev(d_y[0].data_ptr(), n, d_index.data_ptr())
+            else:
+                ctx.liability_split_dev(d_y[0].data_ptr(), n, max_ncon, d_is_case.data_ptr())
 
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
@@ -345,7 +350,7 @@ def run_ours(args, w):
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
     prof = {name: ctx.profile_read(i) for name, i in (("counts", 0), ("pheno_exact", 1), ("lut_main", 2),
-                                                     ("lut_build", 3), ("lut_reduce", 4), ("fused", 7))}
+                                                     ("lut_build", 3), ("lut_reduce", 4), ("cc_order", 6), ("fused", 7))}
     ctx.profile_enable(False)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -523,6 +528,8 @@ def main():
                          ".bed slice row-major with a causal row list")
     ap.add_argument("--fused", action="store_true",
                     help="one pass over HBM: simu_b200_find_freq_pheno (counts + effect scaling + lookups in one kernel)")
+    ap.add_argument("--cc-sort", action="store_true",
+                    help="--cc workloads: full liability argsort (needed when --ncas/--ncon select a subset) instead of the split")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()

@@ -224,6 +224,16 @@ SIMU_B200_API int simu_b200_scale_effects(simu_b200_ctx *ctx, int op, const doub
 SIMU_B200_API int simu_b200_liability_order(simu_b200_ctx *ctx, const double *pheno, int64_t n,
                                             int32_t *index);
 
+/* The two pools of apply_liability_threshold without the full sort: is_case[i] = 0 for the
+ * max_ncon samples of lowest liability -- ranks [0, max_ncon) of the order above, the control
+ * pool of source.cc:1042 -- and 1 for the case pool (:1043).  Enough whenever every sample of a
+ * pool is labelled (the default --ncas / --ncon: source.cc:613-628), because the shuffles of
+ * :1046-1047 then only consume RNG state; with fewer cases / controls requested the labels depend
+ * on the order itself and simu_b200_liability_order is needed.  An 8-pass radix select on the
+ * device instead of an 8-pass radix sort. */
+SIMU_B200_API int simu_b200_liability_split(simu_b200_ctx *ctx, const double *pheno, int64_t n, int64_t max_ncon,
+                                            uint8_t *is_case);
+
 /* ------------------------------------------ hot path, device-resident variants
  * Same operations with DEVICE pointers, asynchronous on the context stream:
  * for callers that keep x, freq and y in HBM (multi-GPU partial sums followed
@@ -249,6 +259,8 @@ SIMU_B200_API int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, doub
                                              const double *d_noise, const double *d_sumsq, double *d_coef);
 SIMU_B200_API int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,
                                                 int32_t *d_index);
+SIMU_B200_API int simu_b200_liability_split_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,
+                                                int64_t max_ncon, uint8_t *d_is_case);
 /* d_s_pow: [2][num_components] exponents (trait 1 then trait 2); *d_bad_index must hold
  * UINT64_MAX on entry and receives the smallest index with het < FLT_EPSILON, if any. */
 SIMU_B200_API int simu_b200_scale_effects_dev(simu_b200_ctx *ctx, int op, const double *d_freq, double *d_effect1,

@@ -53,6 +53,8 @@ SIGNATURES = {
     "simu_b200_apply_heritability": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp, _i64,
                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "simu_b200_liability_order": (_i32, [_vp, _vp, _i64, _vp]),
+    "simu_b200_liability_split": (_i32, [_vp, _vp, _i64, _i64, _vp]),
+    "simu_b200_liability_split_dev": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "simu_b200_scale_effects": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, C.POINTER(C.c_int64)]),
     "simu_b200_scale_effects_dev": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "simu_b200_find_freq_dev": (_i32, [_vp, _vp, _i64, _vp, _vp]),
@@ -294,6 +296,13 @@ class Context:
         self._check(self.lib.simu_b200_liability_order(self.h, _np_ptr(y), y.size, _np_ptr(idx)))
         return idx
 
+    def liability_split(self, pheno, max_ncon: int) -> np.ndarray:
+        """-> uint8 flags: 0 = control pool (the max_ncon lowest liabilities), 1 = case pool."""
+        y = np.ascontiguousarray(pheno, dtype=np.float64)
+        flags = np.empty(y.size, dtype=np.uint8)
+        self._check(self.lib.simu_b200_liability_split(self.h, _np_ptr(y), y.size, max_ncon, _np_ptr(flags)))
+        return flags
+
     # -- hot path, device pointers (ints) -------------------------------------
     def find_freq_dev(self, d_rows, mc, d_counts, d_freq):
         self._check(self.lib.simu_b200_find_freq_dev(self.h, C.c_void_p(d_rows or 0), mc, C.c_void_p(d_counts or 0),
@@ -317,6 +326,9 @@ class Context:
     def heritability_dev(self, hsq, d_y, n, d_noise, d_sumsq, d_coef):
         self._check(self.lib.simu_b200_heritability_dev(self.h, hsq, C.c_void_p(d_y), n, C.c_void_p(d_noise),
                                                         C.c_void_p(d_sumsq), C.c_void_p(d_coef or 0)))
+
+    def liability_split_dev(self, d_pheno, n, max_ncon, d_is_case):
+        self._check(self.lib.simu_b200_liability_split_dev(self.h, C.c_void_p(d_pheno), n, max_ncon, C.c_void_p(d_is_case)))
 
     def liability_order_dev(self, d_pheno, n, d_index):
         self._check(self.lib.simu_b200_liability_order_dev(self.h, C.c_void_p(d_pheno), n, C.c_void_p(d_index)))

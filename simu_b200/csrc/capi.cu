@@ -147,7 +147,7 @@ void simu_b200_close(simu_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->panel) cudaFree(ctx->panel);
-    for (int i = 0; i < 16; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 20; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->dstage[i]) cudaFree(ctx->dstage[i]);
@@ -601,6 +601,15 @@ int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64
     return launch_heritability(ctx, hsq, d_y, n, d_noise, d_sumsq, d_coef);
 }
 
+int simu_b200_liability_split_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n, int64_t max_ncon, uint8_t *d_is_case)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!d_pheno || !d_is_case || max_ncon < 0 || max_ncon > n)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "liability_split: bad arguments");
+    return launch_liability_split(ctx, d_pheno, n, max_ncon, d_is_case);
+}
+
 int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n, int32_t *d_index)
 {
     if (!ctx) return SIMU_B200_EINVAL;
@@ -863,6 +872,23 @@ int simu_b200_scale_effects_dev(simu_b200_ctx *ctx, int op, const double *d_freq
         return ctx_fail(ctx, SIMU_B200_EINVAL, "scale_effects_dev: bad arguments");
     return launch_scale_effects(ctx, d_freq, d_effect1, d_effect2, mc, d_component, d_s_pow, num_components, op,
                                 (unsigned long long *)d_bad_index);
+}
+
+int simu_b200_liability_split(simu_b200_ctx *ctx, const double *pheno, int64_t n, int64_t max_ncon, uint8_t *is_case)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!pheno || !is_case || n <= 0 || max_ncon < 0 || max_ncon > n)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "liability_split: bad arguments");
+    void *d_y = nullptr;
+    int rc;
+    if ((rc = h2d(ctx, SCR_Y1, pheno, (size_t)n * 8, &d_y))) return rc;
+    uint8_t *d_flag = (uint8_t *)ctx_scratch(ctx, SCR_COUNTS, (size_t)n);
+    if (!d_flag) return SIMU_B200_ENOMEM;
+    if ((rc = launch_liability_split(ctx, (const double *)d_y, n, max_ncon, d_flag))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(is_case, d_flag, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return SIMU_B200_OK;
 }
 
 int simu_b200_liability_order(simu_b200_ctx *ctx, const double *pheno, int64_t n, int32_t *index)

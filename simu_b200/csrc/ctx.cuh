@@ -36,8 +36,8 @@ struct simu_b200_ctx {
     bool dstage_used[2] = {false, false};
 
     // grow-on-demand device scratch
-    void *scratch[16] = {nullptr};
-    size_t scratch_bytes[16] = {0};
+    void *scratch[20] = {nullptr};
+    size_t scratch_bytes[20] = {0};
 
     // optional per-kernel device timing (CUDA events on the launching stream)
     bool prof_on = false;
@@ -57,7 +57,7 @@ struct simu_b200_ctx {
 
 enum ScratchSlot {
     SCR_ROWS = 0, SCR_COUNTS, SCR_FREQ, SCR_X1, SCR_X2, SCR_Y1, SCR_Y2, SCR_NOISE,
-    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW
+    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG
 };
 
 int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...);
@@ -102,6 +102,8 @@ int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out
 int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
                         const double *d_sumsq, double *d_coef);
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index);
+// is_case[i] = 0 for the max_ncon samples of lowest liability (ties: lowest index first), 1 for the rest
+int launch_liability_split(simu_b200_ctx *ctx, const double *d_pheno, int64_t n, int64_t max_ncon, uint8_t *d_is_case);
 // effect-size scaling by het^S / sqrt(het).  d_spow: [2][ncomp]; *d_bad: first variant with zero het
 int launch_scale_effects(simu_b200_ctx *ctx, const double *d_freq, double *d_x1, double *d_x2, int64_t mc,
                          const int32_t *d_comp, const double *d_spow, int ncomp, int op, unsigned long long *d_bad);

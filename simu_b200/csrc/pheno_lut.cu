@@ -1207,7 +1207,7 @@ int run_fused(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double
     if (const char *e = getenv("SIMU_B200_FUSED_LOOKAHEAD")) p.lookahead = std::max(1, atoi(e));
     p.dbg = nullptr;
     if (getenv("SIMU_B200_FUSED_DEBUG")) {
-        p.dbg = (unsigned long long *)ctx_scratch(ctx, SCR_SPOW + 0, 4096) + 256;   // tail of a small scratch (debug only)
+        p.dbg = (unsigned long long *)ctx_scratch(ctx, SCR_DEBUG, 256);
         CUDA_TRY(ctx, cudaMemsetAsync(p.dbg, 0, 128, ctx->stream));
     }
     const int threads = (nW * SPLIT + 2 + kCounterWarps) * 32;

@@ -224,13 +224,169 @@ constexpr int kCoopWarps = 8;
 // kCoopTile = keys per warp-tile (all loaded into registers before they are used): 256 for
 // N <= 200K (more warps, shorter dependent chains), 1024 above (fewer histogram columns to scan)
 
+// ------------------------------------------------------ liability threshold (order statistic)
+//
+// apply_liability_threshold (source.cc:1031-1055) sorts the samples by liability and calls ranks
+// [0, max_ncon) the control pool, the rest the case pool.  With the default --ncas / --ncon every
+// sample of a pool is labelled (the shuffles only consume RNG state), so all that matters is on
+// which side of the max_ncon-th order statistic a sample falls.  This kernel finds that statistic
+// with an MSB-first radix select on the order-preserving 64-bit keys (8 passes, each a 256-bin
+// histogram of the keys that still match the prefix) and marks the pools; ties at the threshold go
+// to the controls in ascending sample index -- the order the stable argsort above defines.  One cooperative launch, 9 grid syncs, ~G x 256 global atomics per
+// pass, against 25 grid syncs and 8 scatter passes for the full argsort.
+constexpr int kSelThreads = 1024;
+constexpr int kSelKeys = 4;        // keys a thread keeps in registers across the 8 passes (CACHED variant)
+
+// Grid-wide barrier for a cooperative launch (all blocks co-resident): one arrival counter, monotonically
+// growing targets.  ~1.5 us against ~8 us measured for cooperative_groups' grid.sync() on this part.
+__device__ __forceinline__ void grid_barrier(uint32_t *counter, uint32_t target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+template <bool CACHED>
+__global__ void __launch_bounds__(kSelThreads)
+liability_split_kernel(const double *__restrict__ y, int64_t n, int64_t k, uint32_t *ghist /* [8][256] + barrier word, zeroed */,
+                       uint32_t *geq /* [gridDim.x] */, uint8_t *__restrict__ is_case)
+{
+    uint32_t *barrier = ghist + 8 * 256;
+    uint32_t phase = 0;
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t warp_sums[kSelThreads / 32];
+    __shared__ uint64_t s_prefix;
+    __shared__ int64_t s_rank;
+    const int lane = threadIdx.x & 31;
+    const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= 0 || k >= n) {                           // empty control or case pool: no threshold
+        for (int64_t i = gtid; i < n; i += gthreads) is_case[i] = k <= 0;
+        return;
+    }
+    uint64_t prefix = 0;                              // the threshold key T = key of rank k, found digit by digit
+    int64_t rank = k;                                 // rank of T among the keys that match the prefix
+    // CACHED: the grid covers all keys with kSelKeys per thread, loaded once (n <= grid * 1024 * kSelKeys)
+    uint64_t mykeys[kSelKeys];
+    if (CACHED) {
+#pragma unroll
+        for (int u = 0; u < kSelKeys; u++) {
+            const int64_t i = ((int64_t)blockIdx.x * kSelKeys + u) * blockDim.x + threadIdx.x;
+            mykeys[u] = i < n ? f64_sort_key(y[i]) : 0;
+        }
+    }
+    auto tally = [&](const bool ok, const uint64_t key, const int pass, const int shift) {
+        const bool match = ok && (pass == 7 || (key >> (shift + 8)) == (prefix >> (shift + 8)));
+        const uint32_t d = match ? (uint32_t)((key >> shift) & 0xFF) : 256u;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);               // one atomic per distinct digit and warp
+        if (match && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+    };
+    for (int pass = 7; pass >= 0; pass--) {
+        const int shift = 8 * pass;
+        for (int d = threadIdx.x; d < 256; d += blockDim.x) hist[d] = 0;
+        __syncthreads();
+        if (CACHED) {
+#pragma unroll
+            for (int u = 0; u < kSelKeys; u++)
+                tally(((int64_t)blockIdx.x * kSelKeys + u) * blockDim.x + threadIdx.x < n, mykeys[u], pass, shift);
+        } else {
+            for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < n; i0 += gthreads) {
+                const int64_t i = i0 + threadIdx.x;
+                tally(i < n, i < n ? f64_sort_key(y[i]) : 0, pass, shift);
+            }
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < 256; d += blockDim.x)
+            if (hist[d]) atomicAdd(&ghist[pass * 256 + d], hist[d]);
+        grid_barrier(barrier, ++phase * gridDim.x);
+        if (threadIdx.x < 32) {                       // every block picks the digit for itself
+            int64_t carry = 0, found_rank = -1;
+            uint32_t found_d = 0;
+            uint32_t bins[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) bins[q] = __ldcg(&ghist[pass * 256 + 32 * q + lane]);   // one L2 round trip
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int d0 = 32 * q;
+                const uint32_t v = bins[q];
+                uint32_t incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                const bool here = found_rank < 0 && carry + incl > rank;      // first bin whose cumulative count exceeds rank
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, here);
+                if (found_rank < 0 && ballot) {
+                    const int src = __ffs(ballot) - 1;
+                    const uint32_t excl = __shfl_sync(0xFFFFFFFFu, incl - v, src);
+                    found_d = (uint32_t)(d0 + src);
+                    found_rank = rank - (carry + excl);
+                }
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+            if (lane == 0) { s_prefix = prefix | ((uint64_t)found_d << shift); s_rank = found_rank; }
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        rank = s_rank;                                // = number of keys equal so far that sort before rank k
+        __syncthreads();
+    }
+    // prefix = T; rank = how many of the keys equal to T belong to the controls (lowest sample indices first).
+    // Each block owns a contiguous range of samples, each thread a contiguous sub-range.
+    const int64_t per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per_block, hi = min(n, lo + per_block);
+    const int64_t per_thread = (per_block + blockDim.x - 1) / blockDim.x;
+    const int64_t tlo = min(hi, lo + (int64_t)threadIdx.x * per_thread), thi = min(hi, tlo + per_thread);
+    uint32_t eq = 0;
+    for (int64_t i = tlo; i < thi; i++) eq += f64_sort_key(y[i]) == prefix;
+    // block-wide exclusive scan of eq
+    uint32_t incl = eq;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t v = warp_sums[lane];
+        uint32_t w = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_sums[lane] = w - v;
+        if (lane == 31) geq[blockIdx.x] = w;
+    }
+    __syncthreads();
+    const uint32_t before_in_block = warp_sums[threadIdx.x >> 5] + incl - eq;
+    grid_barrier(barrier, ++phase * gridDim.x);
+    int64_t before = before_in_block;
+    for (unsigned b = 0; b < blockIdx.x; b++) before += __ldcg(&geq[b]);
+    for (int64_t i = tlo; i < thi; i++) {
+        const uint64_t key = f64_sort_key(y[i]);
+        bool control = key < prefix;
+        if (key == prefix) { control = before < rank; before++; }
+        is_case[i] = !control;
+    }
+}
+
 template <int kCoopTile>
 __global__ void __launch_bounds__(kCoopWarps * 32)
 sort_coop_kernel(const double *__restrict__ y, int64_t n, uint64_t *k0, uint64_t *k1, int32_t *v0, int32_t *v1,
-                 uint32_t *hist, int64_t tiles, int32_t *out_index)
+                 uint32_t *hist, int64_t tiles, int32_t *out_index, uint32_t *barrier /* zeroed */)
 {
+    uint32_t phase = 0;
     constexpr int kCoopPer = kCoopTile / 32;
-    cg::grid_group grid = cg::this_grid();
     __shared__ uint32_t cnt[kCoopWarps][256];
     __shared__ uint32_t digit_base[256];
     uint32_t *digit_total = hist + tiles * 256;       // 256 extra words behind the histograms
@@ -242,7 +398,7 @@ sort_coop_kernel(const double *__restrict__ y, int64_t n, uint64_t *k0, uint64_t
         k0[i] = f64_sort_key(y[i]);
         v0[i] = (int32_t)i;
     }
-    grid.sync();
+    grid_barrier(barrier, ++phase * gridDim.x);
 
     for (int pass = 0; pass < 8; pass++) {
         const int shift = 8 * pass;
@@ -261,7 +417,7 @@ sort_coop_kernel(const double *__restrict__ y, int64_t n, uint64_t *k0, uint64_t
             for (int d = lane; d < 256; d += 32) hist[(int64_t)d * tiles + tile] = cnt[warp][d];
             __syncwarp();
         }
-        grid.sync();
+        grid_barrier(barrier, ++phase * gridDim.x);
         // ---- exclusive scan over (digit major, tile minor): every warp of the grid scans the tiles
         // of some digits (coalesced loads + shuffles) and records the digit totals ...
         for (int64_t d = gwarp; d < 256; d += gwarps) {
@@ -280,7 +436,7 @@ sort_coop_kernel(const double *__restrict__ y, int64_t n, uint64_t *k0, uint64_t
             }
             if (lane == 0) digit_total[d] = carry;
         }
-        grid.sync();
+        grid_barrier(barrier, ++phase * gridDim.x);
         // ... which every block scans for itself (256 values) before scattering
         if (warp == 0) {
             uint32_t carry = 0;
@@ -328,7 +484,7 @@ sort_coop_kernel(const double *__restrict__ y, int64_t n, uint64_t *k0, uint64_t
             }
             __syncwarp();
         }
-        grid.sync();
+        grid_barrier(barrier, ++phase * gridDim.x);
         uint64_t *tk = k0; k0 = k1; k1 = tk;
         int32_t *tv = v0; v0 = v1; v1 = tv;
     }
@@ -368,6 +524,28 @@ int launch_scale_effects(simu_b200_ctx *ctx, const double *d_freq, double *d_x1,
     return ctx_cuda(ctx, cudaGetLastError(), "scale_effects_kernel launch");
 }
 
+int launch_liability_split(simu_b200_ctx *ctx, const double *d_pheno, int64_t n, int64_t max_ncon, uint8_t *d_is_case)
+{
+    if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "liability_split: n must be positive");
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (!coop) return ctx_fail(ctx, SIMU_B200_ECUDA, "liability_split: device lacks cooperative launch");
+    const int64_t per_block = (int64_t)kSelThreads * kSelKeys;
+    const bool cached = (n + per_block - 1) / per_block <= ctx->num_sms;      // every key in a register of some thread
+    const int64_t blocks = cached ? (n + per_block - 1) / per_block : ctx->num_sms;
+    uint32_t *scr = (uint32_t *)ctx_scratch(ctx, SCR_SORT, (size_t)(8 * 256 + 32 + ctx->num_sms) * 4);
+    if (!scr) return SIMU_B200_ENOMEM;
+    CUDA_TRY(ctx, cudaMemsetAsync(scr, 0, (8 * 256 + 32) * 4, ctx->stream));      // histograms + the barrier word
+    uint32_t *ghist = scr, *geq = scr + 8 * 256 + 32;
+    void *args[] = {(void *)&d_pheno, (void *)&n, (void *)&max_ncon, (void *)&ghist, (void *)&geq, (void *)&d_is_case};
+    const int ps = prof_begin(ctx, PROF_SORT);
+    cudaError_t e = cudaLaunchCooperativeKernel(cached ? (void *)liability_split_kernel<true> : (void *)liability_split_kernel<false>,
+                                                dim3((unsigned)blocks), dim3(kSelThreads), args, 0, ctx->stream);
+    prof_end(ctx, ps);
+    ctx->launches++;
+    return ctx_cuda(ctx, e, "liability_split launch");
+}
+
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index)
 {
     if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "argsort: n must be positive");
@@ -393,8 +571,11 @@ int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32
         int64_t ctiles = (n + tile - 1) / tile;
         int64_t blocks = (ctiles + kCoopWarps - 1) / kCoopWarps;
         blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, ctx->coop_sort_blocks));
+        uint32_t *barrier = (uint32_t *)ctx_scratch(ctx, SCR_SYNC, 256);
+        if (!barrier) return SIMU_B200_ENOMEM;
+        CUDA_TRY(ctx, cudaMemsetAsync(barrier, 0, 4, ctx->stream));
         void *args[] = {(void *)&d_key, (void *)&n, (void *)&k0, (void *)&k1, (void *)&v0, (void *)&v1,
-                        (void *)&hist, (void *)&ctiles, (void *)&d_index};
+                        (void *)&hist, (void *)&ctiles, (void *)&d_index, (void *)&barrier};
         const int ps = prof_begin(ctx, PROF_SORT);
         void *kern = tile == 256 ? (void *)sort_coop_kernel<256> : (void *)sort_coop_kernel<1024>;
         cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)blocks), dim3(kCoopWarps * 32), args, 0, ctx->stream);

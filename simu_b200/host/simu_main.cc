@@ -527,8 +527,6 @@ void apply_heritability(float hsq, Mt19937 &rng, Gpu &gpu, std::vector<double> *
 void apply_liability_threshold(float k, int ncas, int ncon, Mt19937 &rng, Gpu &gpu, std::vector<double> *pheno)
 {                                                                                                // source.cc:1031-1055
     const int n = static_cast<int>(pheno->size());
-    std::vector<int32_t> index(n);
-    gpu.check(simu_b200_liability_order(gpu.ctx, pheno->data(), n, index.data()));
     const int max_ncas = (int)floor(k * n), max_ncon = n - max_ncas;
     std::vector<int> cas_inds, con_inds;
     for (int i = 0; i < max_ncon; i++) con_inds.push_back(i);
@@ -537,6 +535,16 @@ void apply_liability_threshold(float k, int ncas, int ncon, Mt19937 &rng, Gpu &g
     random_shuffle(cas_inds, rng);
     if ((int)con_inds.size() < ncon) throw std::runtime_error("ERROR: too many controls requested");
     if ((int)cas_inds.size() < ncas) throw std::runtime_error("ERROR: too many cases requested");
+    if (ncon == max_ncon && ncas == max_ncas) {
+        // every sample of both pools is labelled (the default, source.cc:613-628): the shuffles above only
+        // consumed RNG state and the pools follow from the order statistic -- radix select instead of a sort
+        std::vector<uint8_t> is_case(n);
+        gpu.check(simu_b200_liability_split(gpu.ctx, pheno->data(), n, max_ncon, is_case.data()));
+        for (int i = 0; i < n; i++) pheno->at(i) = is_case[i] ? 2 : 1;
+        return;
+    }
+    std::vector<int32_t> index(n);
+    gpu.check(simu_b200_liability_order(gpu.ctx, pheno->data(), n, index.data()));
     for (int i = 0; i < n; i++) pheno->at(i) = -9;
     for (int i = 0; i < ncon; i++) pheno->at(index[con_inds[i]]) = 1;
     for (int i = 0; i < ncas; i++) pheno->at(index[cas_inds[i]]) = 2;

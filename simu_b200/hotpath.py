@@ -176,7 +176,6 @@ class HotPath:
         -> labels (1 control, 2 case, -9 unused) as float64."""
         y = np.asarray(pheno_per_sample, dtype=np.float64)
         n = int(y.size)
-        index = self.ctx.liability_order(y)                               # :1032-1034
         max_ncas = int(math.floor(float(np.float32(k) * np.float32(n))))  # :1038 (float product)
         max_ncon = n - max_ncas                                           # :1039
         con_inds = list(range(0, max_ncon))                               # :1042
@@ -187,6 +186,11 @@ class HotPath:
             raise RuntimeError("ERROR: too many controls requested")      # :1049
         if len(cas_inds) < ncas:
             raise RuntimeError("ERROR: too many cases requested")         # :1050
+        if ncon == max_ncon and ncas == max_ncas:
+            # every sample of both pools is labelled (the default): the shuffles only consumed RNG
+            # state, and the pools follow from the order statistic alone -- radix select, no sort
+            return np.where(self.ctx.liability_split(y, max_ncon) != 0, 2.0, 1.0)
+        index = self.ctx.liability_order(y)                               # :1032-1034
         out = np.full(n, -9.0)                                            # :1052
         out[index[np.asarray(con_inds[:ncon], dtype=np.int64)]] = 1       # :1053
         out[index[np.asarray(cas_inds[:ncas], dtype=np.int64)]] = 2       # :1054

@@ -350,6 +350,52 @@ def test_liability_order_bit_exact(n):
         assert np.array_equal(idx, oracle.liability_order(y))
 
 
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 1000, 1025, 4097, 16385, 100000, 500001, 700001])
+def test_liability_split_matches_the_sorted_order(n):
+    """The radix-select split (order statistic) gives the same two pools as ranks [0, k) / [k, n) of
+    the stable argsort, for every k incl. the ends, with ties, signed zeros and infinities."""
+    rng = np.random.default_rng(n + 1)
+    y = rng.standard_normal(n)
+    if n > 10:
+        y[rng.integers(0, n, n // 4)] = 0.25                       # a big tie class
+        y[rng.integers(0, n, n // 50 + 1)] = -1.5
+        y[rng.integers(0, n, 3)] = -0.0
+        y[rng.integers(0, n, 3)] = 0.0
+        y[0], y[1] = np.inf, -np.inf
+    with capi.Context(max(n, 4)) as ctx:
+        idx = ctx.liability_order(y)
+        ks = sorted({0, 1, n // 10, n // 2, max(0, n - 1), n, int(np.searchsorted(np.sort(y), 0.25)) + 7})
+        for k in ks:
+            if k > n:
+                continue
+            flags = ctx.liability_split(y, k)
+            want = np.ones(n, np.uint8)
+            want[idx[:k]] = 0
+            assert np.array_equal(flags, want), (n, k)
+
+
+def test_liability_threshold_default_pools_use_the_split():
+    """Default --ncas/--ncon (every sample labelled): the mirror's labels from the split equal the
+    oracle's labels from the full sort; the shuffles are still drawn (RNG state)."""
+    n, k = 20000, 0.1
+    y = np.random.default_rng(4).standard_normal(n)
+    calls = []
+
+    def shuffle(lst):
+        calls.append(len(lst))
+        a = np.array(lst); np.random.default_rng(len(lst)).shuffle(a)
+        return a.tolist()
+
+    max_cas, max_con = oracle.liability_split(k, n)
+    with capi.Context(n) as ctx:
+        lab = HotPath(ctx).apply_liability_threshold(k, max_cas, max_con, shuffle, y)
+    assert calls == [max_con, max_cas]
+    con = np.arange(max_con); np.random.default_rng(max_con).shuffle(con)
+    cas = np.arange(max_con, n); np.random.default_rng(max_cas).shuffle(cas)
+    olab = oracle.liability_labels(k, max_cas, max_con, oracle.liability_order(y), con, cas)
+    assert np.array_equal(lab, olab) and np.count_nonzero(lab == 2) == max_cas
+
+
 def test_liability_threshold_labels_agree_with_oracle():
     n = 5000
     rng = np.random.default_rng(9)
