@@ -45,6 +45,26 @@ private:
 
 bool file_exists(const std::string &p) { struct stat st; return stat(p.c_str(), &st) == 0; }
 
+// SIMU_B200_TIMING=1: wall time per stage as one JSON line on stderr (the .log and stdout stay as the reference's)
+struct StageTimer {
+    std::vector<std::pair<std::string, double>> stages;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void mark(const char *name)
+    {
+        const auto t1 = std::chrono::steady_clock::now();
+        stages.emplace_back(name, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+    void report() const
+    {
+        if (!getenv("SIMU_B200_TIMING")) return;
+        double total = 0;
+        std::cerr << "{";
+        for (const auto &s : stages) { std::cerr << "\"" << s.first << "_s\": " << s.second << ", "; total += s.second; }
+        std::cerr << "\"total_s\": " << total << "}\n";
+    }
+};
+
 std::string now_string(std::time_t t)            // boost::posix_time::ptime operator<<: 2018-Jan-01 12:00:00
 {
     char buf[64];
@@ -644,8 +664,10 @@ int main(int argc, char *argv[])
             const std::time_t started = std::time(nullptr);
             log << "Analysis started: " << now_string(started) << "\n";
 
+            StageTimer timer;
             PlinkFiles pio;
             fix_and_validate(o, log, &pio);
+            timer.mark("parse_and_validate");
             describe_simu_options(o, log);
 
             Mt19937 rng(o.seed);                                                          // source.cc:1222
@@ -654,12 +676,15 @@ int main(int argc, char *argv[])
             if (o.trait2_snp_offset == 0) find_causals(o, rng, log, pio, &comp, &effect1, &effect2);
             else find_causals_trait2_snp_offset(o, rng, &comp);
 
+            timer.mark("causal_selection");
             Gpu gpu;
             gpu.open(o.num_samples);
+            timer.mark("cuda_context");
 
             log << "Calculate allele frequencies (for causal markers only)... \n";
             std::vector<double> freq_vec;
             find_freq(o, comp, pio, gpu, &freq_vec);
+            timer.mark("stage_bed_and_find_freq");
 
             auto het_or_throw = [&](int v, const char *what) {                            // source.cc:1249-1255
                 const double freq = freq_vec[v], het = fabs(2 * freq * (1 - freq));
@@ -711,9 +736,11 @@ int main(int argc, char *argv[])
                 }
             }
 
+            timer.mark("effect_sizes");
             log << "Calculate phenotypes... \n";
             std::vector<double> pheno1, pheno2;
             find_pheno(o, freq_vec, effect1, effect2, gpu, &pheno1, &pheno2);
+            timer.mark("find_pheno");
 
             apply_heritability(o.hsq[0], rng, gpu, &pheno1, &effect1);                    // source.cc:1299-1300
             if (o.num_traits == 2) apply_heritability(o.hsq[1], rng, gpu, &pheno2, &effect2);
@@ -723,6 +750,7 @@ int main(int argc, char *argv[])
                 if (o.num_traits == 2) apply_liability_threshold(o.k[1], o.ncas[1], o.ncon[1], rng, gpu, &pheno2);
             }
 
+            timer.mark("heritability_and_threshold");
             log << "Save phenotypes to " << o.out_pheno << "...\n";
             save_pheno_file(o, pio, pheno1, pheno2);
             log << "Save causal variants and their effect sizes to " << o.out << ((o.num_traits == 2) ? ".*" : ".1")
@@ -730,6 +758,8 @@ int main(int argc, char *argv[])
             save_causals_file(o, o.out_causals[0], pio, freq_vec, comp, effect1);
             if (o.num_traits == 2) save_causals_file(o, o.out_causals[1], pio, freq_vec, comp, effect2);
 
+            timer.mark("write_outputs");
+            timer.report();
             const std::time_t finished = std::time(nullptr);
             log << "Analysis finished: " << now_string(finished) << "\n";
             log << "Elapsed time: " << duration_string((long)(finished - started)) << "\n";
