@@ -527,7 +527,8 @@ def main():
                     help="HBM panel: compact causal rows in GROUP4 layout (what the CLI stages) or the whole "
                          ".bed slice row-major with a causal row list")
     ap.add_argument("--fused", action="store_true",
-                    help="one pass over HBM: simu_b200_find_freq_pheno (counts + effect scaling + lookups in one kernel)")
+                    help="one call: simu_b200_find_freq_pheno (counts + effect scaling + lookups on the device; "
+                         "SIMU_B200_FUSED_IMPL=onepass selects the experimental single-kernel version)")
     ap.add_argument("--cc-sort", action="store_true",
                     help="--cc workloads: full liability argsort (needed when --ncas/--ncon select a subset) instead of the split")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

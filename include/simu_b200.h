@@ -177,9 +177,13 @@ SIMU_B200_API int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, 
                                        const double *freq, const double *effect1, const double *effect2,
                                        double *pheno1, double *pheno2, int mode);
 
-/* find_freq + effect scaling + find_pheno (FAST mode) in ONE pass over the panel: the fused
- * kernel counts a row block a few steps before it looks it up, so HBM is read once instead of
- * twice.  GROUP4 panels only; rows 0..mc-1.  It replaces this stretch of main():
+/* find_freq + effect scaling + find_pheno (FAST mode) behind ONE call, everything on the device
+ * (no host round trip between the passes).  GROUP4 panels only; rows 0..mc-1.  Default
+ * implementation: the standard kernels back to back (SIMU_B200_OVERLAP_MB=<n> pipelines them in
+ * chunks over two streams); SIMU_B200_FUSED_IMPL=onepass selects the experimental single
+ * persistent kernel that counts a row block a few steps before it looks it up, so that HBM is read
+ * once instead of twice (needs N < 2^19; parity-green but slower today).
+ * The call replaces this stretch of main():
  *     find_freq(...)                                   source.cc:1235
  *     draw / read effect sizes, scale them by het      source.cc:1238-1290
  *     find_pheno(...)                                  source.cc:1295

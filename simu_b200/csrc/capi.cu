@@ -161,6 +161,8 @@ void simu_b200_close(simu_b200_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -718,6 +720,12 @@ int simu_b200_find_freq_pheno_dev(simu_b200_ctx *ctx, int64_t mc, const double *
         if (d_pheno2) CUDA_TRY(ctx, cudaMemsetAsync(d_pheno2, 0, (size_t)ctx->n_samples * 8, ctx->stream));
         return SIMU_B200_OK;
     }
+    // implementations: "overlap" (default) = the existing kernels as a chunked two-stream pipeline;
+    // "onepass" = the experimental single persistent kernel (HBM read once, slower today)
+    const char *impl = getenv("SIMU_B200_FUSED_IMPL");
+    if (!impl || strcmp(impl, "onepass") != 0)
+        return launch_pheno_overlap(ctx, mc, d_raw1, d_raw2, scale_op, d_component, d_s_pow, num_components, d_counts, d_freq,
+                                    d_effect1, d_effect2, d_pheno1, d_pheno2, (unsigned long long *)d_bad_index);
     int fused = 1;
     if (const char *e = getenv("SIMU_B200_FUSED_PREBUILT")) fused = atoi(e) ? 0 : 1;   // A/B: same schedule, two passes
     if (!fused) {

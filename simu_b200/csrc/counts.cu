@@ -110,7 +110,7 @@ counts_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_
 {
     __shared__ uint32_t part[8][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kGroupsPerCta = 8 / SPLIT;
+    const int kGroupsPerCta = (int)(blockDim.x >> 5) / SPLIT;   // 8 warps per CTA (4 when launched beside a lookup CTA)
     constexpr int kStride = 32 * SPLIT;                    // vectors between two loads of a lane
     const int sub = warp % SPLIT, gslot = warp / SPLIT;
     const int64_t ngroups = (mc + 3) >> 2;
@@ -166,32 +166,47 @@ counts_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, int64_
 
 }  // namespace
 
+// GROUP4 counts of mc rows that start at `first_group` (rows 4*first_group ..), on an explicit stream
+int launch_counts_g4_range(simu_b200_ctx *ctx, cudaStream_t stream, int64_t first_group, int64_t mc, int32_t *d_counts,
+                           double *d_freq, int threads)
+{
+    if (mc <= 0) return SIMU_B200_OK;
+    const int warps_per_block = threads / 32;               // 8, or 4 to squeeze in beside a resident lookup CTA
+    const int64_t max_blocks = (int64_t)ctx->num_sms * 8;   // 64 resident warps per SM
+    // one warp per 4-row group; when the groups do not fill the resident warps, 2/4/8 warps
+    // of a CTA share a group (more loads in flight per group row)
+    const int64_t groups = (mc + 3) >> 2;
+    const int64_t resident = max_blocks * 8;
+    int split = 1;
+    while (split < warps_per_block && groups * split * 2 <= resident) split *= 2;
+    int64_t blocks = (groups * split + warps_per_block - 1) / warps_per_block;
+    if (blocks > max_blocks) blocks = max_blocks;
+    const uint8_t *base = ctx->panel + first_group * ctx->group_stride;
+#define LAUNCH_G4(S) counts_g4_kernel<S><<<(unsigned)blocks, warps_per_block * 32, 0, stream>>>( \
+        base, ctx->group_stride, mc, ctx->n_samples, d_counts, d_freq)
+    if (split == 1) LAUNCH_G4(1); else if (split == 2) LAUNCH_G4(2); else if (split == 4) LAUNCH_G4(4); else LAUNCH_G4(8);
+#undef LAUNCH_G4
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "counts_g4_kernel launch");
+}
+
 int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts, double *d_freq)
 {
     if (mc <= 0) return SIMU_B200_OK;
-    const int warps_per_block = 8;
-    const int64_t max_blocks = (int64_t)ctx->num_sms * 8;   // 64 resident warps per SM
     const int ps = prof_begin(ctx, PROF_COUNTS);
+    int rc = SIMU_B200_OK;
     if (ctx->layout == SIMU_B200_LAYOUT_GROUP4) {
-        // one warp per 4-row group; when the groups do not fill the resident warps, 2/4/8 warps
-        // of a CTA share a group (more loads in flight per group row)
-        const int64_t groups = (mc + 3) >> 2;
-        const int64_t resident = max_blocks * warps_per_block;
-        int split = 1;
-        while (split < 8 && groups * split * 2 <= resident) split *= 2;
-        int64_t blocks = (groups * split + warps_per_block - 1) / warps_per_block;
-        if (blocks > max_blocks) blocks = max_blocks;
-#define LAUNCH_G4(S) counts_g4_kernel<S><<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>( \
-            ctx->panel, ctx->group_stride, mc, ctx->n_samples, d_counts, d_freq)
-        if (split == 1) LAUNCH_G4(1); else if (split == 2) LAUNCH_G4(2); else if (split == 4) LAUNCH_G4(4); else LAUNCH_G4(8);
-#undef LAUNCH_G4
+        rc = launch_counts_g4_range(ctx, ctx->stream, 0, mc, d_counts, d_freq, 256);
     } else {
+        const int warps_per_block = 8;
+        const int64_t max_blocks = (int64_t)ctx->num_sms * 8;   // 64 resident warps per SM
         int64_t blocks = (mc + warps_per_block - 1) / warps_per_block;
         if (blocks > max_blocks) blocks = max_blocks;
         counts_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, ctx->stream>>>(
             ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_counts, d_freq);
+        ctx->launches++;
+        rc = ctx_cuda(ctx, cudaGetLastError(), "counts_kernel launch");
     }
     prof_end(ctx, ps);
-    ctx->launches++;
-    return ctx_cuda(ctx, cudaGetLastError(), "counts_kernel launch");
+    return rc;
 }

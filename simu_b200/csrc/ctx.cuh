@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/simu_b200.h"
 
@@ -52,6 +53,8 @@ struct simu_b200_ctx {
     int coop_sort_blocks = -1;           // co-resident blocks of the cooperative sort (-1: not queried)
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
+    std::vector<cudaEvent_t> chunk_events;   // overlap pipeline of find_freq_pheno
+    cudaStream_t aux_stream = nullptr;
     std::string err;
 };
 
@@ -81,6 +84,9 @@ void prof_end(simu_b200_ctx *ctx, int slot);
 // kernel (a): per-SNP allele counts + frequency.  counts.cu
 int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t *d_counts, double *d_freq);
 
+int launch_counts_g4_range(simu_b200_ctx *ctx, cudaStream_t stream, int64_t first_group, int64_t mc, int32_t *d_counts,
+                           double *d_freq, int threads);
+
 // kernel (b), exact FP64 ordered mode.  pheno_exact.cu
 int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
                        const double *d_x1, const double *d_x2, double *d_y1, double *d_y2);
@@ -97,6 +103,12 @@ int launch_pheno_fused(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, con
                        double *d_x1, double *d_x2, double *d_y1, double *d_y2, unsigned long long *d_bad, int fused,
                        const double *d_freq_in);
 
+// the same result from the existing kernels as a chunked two-stream pipeline (counts of chunk c+1 beside the
+// lookups of chunk c).  pheno_lut.cu
+int launch_pheno_overlap(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2, int op,
+                         const int32_t *d_comp, const double *d_spow, int ncomp, int32_t *d_counts, double *d_freq,
+                         double *d_x1, double *d_x2, double *d_y1, double *d_y2, unsigned long long *d_bad);
+
 // kernel (c): reductions.  reduce.cu
 int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out);
 int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
@@ -107,6 +119,10 @@ int launch_liability_split(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,
 // effect-size scaling by het^S / sqrt(het).  d_spow: [2][ncomp]; *d_bad: first variant with zero het
 int launch_scale_effects(simu_b200_ctx *ctx, const double *d_freq, double *d_x1, double *d_x2, int64_t mc,
                          const int32_t *d_comp, const double *d_spow, int ncomp, int op, unsigned long long *d_bad);
+// the same on an explicit stream, with `index_base` added to the variant index reported in *d_bad
+int launch_scale_effects_on(simu_b200_ctx *ctx, cudaStream_t stream, const double *d_freq, double *d_x1, double *d_x2,
+                            int64_t mc, const int32_t *d_comp, const double *d_spow, int ncomp, int op,
+                            unsigned long long *d_bad, int64_t index_base);
 
 // staging: move n_rows packed rows (pitch src_pitch) from a device bounce buffer into panel rows
 // [dst_row, dst_row + n_rows) -- re-pitched (ROWS) or sample-interleaved (GROUP4).  stage.cu

@@ -1234,6 +1234,102 @@ int run_fused(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_fused launch");
 }
 
+// ------------------------------------------------- find_freq_pheno from the standard kernels
+//
+// counts -> effect scaling -> table build -> lookups, all on the device, so that one call replaces
+// find_freq + the host's effect scaling + find_pheno without a host round trip in between.
+// SIMU_B200_OVERLAP_MB=<chunk size> turns it into a chunked two-stream pipeline (stream B does
+// counts -> scaling -> tables of chunk c+1 while stream A looks up chunk c; the lookups of all chunks
+// accumulate into the same FP64 slots, reduced once).  The idea: counts_g4 is HBM-bound with idle SM
+// pipes, pheno_lut_g4 shared-memory-bound with ~45 % of HBM idle, and a counts CTA (no shared memory,
+// 20 K registers) fits on an SM beside the resident lookup CTA.  MEASURED (config 2, 1.124 ms as two
+// passes): 3.78 / 2.46 / 1.50 / 1.19 ms with 32 / 64 / 256 / 1300 MB chunks -- ~34 us of launch work per
+// chunk on the CPU, and with few chunks the counts kernel squeezed to one CTA per SM (32 KB in flight
+// instead of 96) runs at a third of its bandwidth and becomes the bottleneck.  So the default is ONE
+// chunk (= the plain sequence); the pipeline stays as an experiment switch.
+template <int K>
+int run_overlap(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2, int op, const int32_t *d_comp,
+                const double *d_spow, int ncomp, int32_t *d_counts, double *d_freq, double *d_x1, double *d_x2,
+                double *d_y1, double *d_y2, unsigned long long *d_bad)
+{
+    const int64_t n = ctx->n_samples;
+    const int64_t tiles = (n + kTileSamples - 1) / kTileSamples;
+    const int64_t npad = tiles * kTileSamples;
+    int64_t chunk_mb = 1 << 24;                        // default: one chunk
+    if (const char *e = getenv("SIMU_B200_OVERLAP_MB")) chunk_mb = std::max(1, atoi(e));
+    int64_t chunk_rows = (chunk_mb << 20) / std::max<int64_t>(1, ctx->group_stride / 4);
+    chunk_rows = std::max<int64_t>(kBlockRows, chunk_rows / kBlockRows * kBlockRows);
+    const int64_t nchunks = (mc + chunk_rows - 1) / chunk_rows;
+    const int64_t nblocks_all = (mc + kBlockRows - 1) / kBlockRows;
+    // pipelined: 8 consumer warps, which leaves registers for a counts CTA on the SM; one chunk: the best kernel
+    const int split = (K == 1 && nchunks == 1) ? 2 : 1;
+    const int64_t steps_max = tiles * ((std::min(mc, chunk_rows) + kBlockRows - 1) / kBlockRows);
+    const int64_t grid_max = std::min<int64_t>(steps_max, ctx->num_sms);
+    const int slots = ((int)((grid_max + tiles - 1) / tiles) + 1) * split;
+
+    float *lut = (float *)ctx_scratch(ctx, SCR_LUT, (size_t)nblocks_all * kTableBytes);
+    const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
+    double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
+    if (!d_freq) d_freq = (double *)ctx_scratch(ctx, SCR_FREQ, (size_t)mc * 8);
+    if (!d_x1) d_x1 = (double *)ctx_scratch(ctx, SCR_X1, (size_t)mc * 8);
+    if (K == 2 && !d_x2) d_x2 = (double *)ctx_scratch(ctx, SCR_X2, (size_t)mc * 8);
+    if (!lut || !ypart || !d_freq || !d_x1 || (K == 2 && !d_x2)) return SIMU_B200_ENOMEM;
+    if (!ctx->lut_attr_set[K]) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_g4_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4Shape<1>::kSmemBytes));
+        if (K == 1)
+            CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_lut_g4_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4Shape<2>::kSmemBytes));
+        ctx->lut_attr_set[K] = true;
+    }
+    if (!ctx->aux_stream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    while ((int64_t)ctx->chunk_events.size() < nchunks + 1) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->chunk_events.push_back(e);
+    }
+    cudaStream_t sA = ctx->stream, sB = nchunks == 1 ? ctx->stream : ctx->aux_stream;   // one chunk: one stream
+    const int ps = prof_begin(ctx, PROF_FUSED);
+    CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, sA));
+    if (sB != sA) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_events[nchunks], sA));      // fork: B starts after everything queued on A
+        CUDA_TRY(ctx, cudaStreamWaitEvent(sB, ctx->chunk_events[nchunks], 0));
+    }
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int64_t r0 = c * chunk_rows, mcc = std::min(chunk_rows, mc - r0);
+        const int64_t b0 = r0 / kBlockRows, nb = (mcc + kBlockRows - 1) / kBlockRows;
+        // ---- stream B: counts -> effect scaling -> tables of chunk c
+        int rc = launch_counts_g4_range(ctx, sB, r0 / 4, mcc, d_counts ? d_counts + 4 * r0 : nullptr, d_freq + r0, 256);
+        if (rc) return rc;
+        if (d_x1 != d_raw1) CUDA_TRY(ctx, cudaMemcpyAsync(d_x1 + r0, d_raw1 + r0, (size_t)mcc * 8, cudaMemcpyDeviceToDevice, sB));
+        if (K == 2 && d_x2 != d_raw2)
+            CUDA_TRY(ctx, cudaMemcpyAsync(d_x2 + r0, d_raw2 + r0, (size_t)mcc * 8, cudaMemcpyDeviceToDevice, sB));
+        if (op >= 0 && (rc = launch_scale_effects_on(ctx, sB, d_freq + r0, d_x1 + r0, K == 2 ? d_x2 + r0 : nullptr, mcc,
+                                                     d_comp ? d_comp + r0 : nullptr, d_spow, ncomp, op, d_bad, r0)))
+            return rc;
+        lut_build_kernel<K><<<(unsigned)nb, 256, 0, sB>>>(d_freq + r0, d_x1 + r0, K == 2 ? d_x2 + r0 : nullptr, mcc,
+                                                          lut + b0 * (kTableBytes / 4));
+        // ---- stream A: lookups of chunk c into the shared slots
+        if (sB != sA) {
+            CUDA_TRY(ctx, cudaEventRecord(ctx->chunk_events[c], sB));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(sA, ctx->chunk_events[c], 0));
+        }
+        LutParams p;
+        p.panel = ctx->panel + (r0 / 4) * ctx->group_stride; p.row_stride = ctx->group_stride; p.rows = nullptr; p.mc = mcc;
+        p.n_samples = n; p.lut = lut + b0 * (kTableBytes / 4); p.ypart = ypart; p.npad = npad; p.tiles = tiles;
+        p.nblocks = nb; p.steps = tiles * nb;
+        const int64_t grid = std::min<int64_t>(p.steps, ctx->num_sms);
+        if (K == 1 && split == 2)
+            pheno_lut_g4_kernel<1, 2><<<(unsigned)grid, G4Shape<2>::kThreads, G4Shape<2>::kSmemBytes, sA>>>(p);
+        else
+            pheno_lut_g4_kernel<K, 1><<<(unsigned)grid, G4Shape<1>::kThreads, G4Shape<1>::kSmemBytes, sA>>>(p);
+        ctx->launches += 2;
+    }
+    lut_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, sA>>>(ypart, npad, n, slots, d_y1, d_y2);
+    prof_end(ctx, ps);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "find_freq_pheno (overlap) launch");
+}
+
 }  // namespace
 
 int launch_pheno_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
@@ -1258,4 +1354,13 @@ int launch_pheno_fused(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, con
                             fused, d_freq_in);
     return run_fused<1>(ctx, mc, d_raw1, nullptr, op, d_comp, d_spow, ncomp, d_counts, d_freq, d_x1, nullptr, d_y1, nullptr,
                         d_bad, fused, d_freq_in);
+}
+
+int launch_pheno_overlap(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2, int op,
+                         const int32_t *d_comp, const double *d_spow, int ncomp, int32_t *d_counts, double *d_freq,
+                         double *d_x1, double *d_x2, double *d_y1, double *d_y2, unsigned long long *d_bad)
+{
+    if (d_raw2 && d_y2)
+        return run_overlap<2>(ctx, mc, d_raw1, d_raw2, op, d_comp, d_spow, ncomp, d_counts, d_freq, d_x1, d_x2, d_y1, d_y2, d_bad);
+    return run_overlap<1>(ctx, mc, d_raw1, nullptr, op, d_comp, d_spow, ncomp, d_counts, d_freq, d_x1, nullptr, d_y1, nullptr, d_bad);
 }

@@ -97,13 +97,13 @@ heritability_kernel(float hsq, double *__restrict__ y, int64_t n, const double *
 __global__ void __launch_bounds__(256)
 scale_effects_kernel(const double *__restrict__ freq, double *__restrict__ x1, double *__restrict__ x2, int64_t mc,
                      const int32_t *__restrict__ comp, const double *__restrict__ spow, int ncomp, int op,
-                     unsigned long long *__restrict__ bad)
+                     unsigned long long *__restrict__ bad, int64_t index_base)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= mc) return;
     const double f = freq[j];
     const double het = fabs(__dmul_rn(__dmul_rn(2.0, f), __dsub_rn(1.0, f)));      // :1250
-    if (op != 2 && het < (double)FLT_EPSILON) { atomicMin(bad, (unsigned long long)j); return; }   // :1251, :1278; none at :1092
+    if (op != 2 && het < (double)FLT_EPSILON) { atomicMin(bad, (unsigned long long)(index_base + j)); return; }   // :1251, :1278; none at :1092
     const int c = comp ? comp[j] : 0;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -514,14 +514,21 @@ int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, c
     return ctx_cuda(ctx, cudaGetLastError(), "heritability launch");
 }
 
+int launch_scale_effects_on(simu_b200_ctx *ctx, cudaStream_t stream, const double *d_freq, double *d_x1, double *d_x2,
+                            int64_t mc, const int32_t *d_comp, const double *d_spow, int ncomp, int op,
+                            unsigned long long *d_bad, int64_t index_base)
+{
+    if (mc <= 0) return SIMU_B200_OK;
+    scale_effects_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, stream>>>(d_freq, d_x1, d_x2, mc, d_comp, d_spow, ncomp, op, d_bad,
+                                                                         index_base);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "scale_effects_kernel launch");
+}
+
 int launch_scale_effects(simu_b200_ctx *ctx, const double *d_freq, double *d_x1, double *d_x2, int64_t mc,
                          const int32_t *d_comp, const double *d_spow, int ncomp, int op, unsigned long long *d_bad)
 {
-    if (mc <= 0) return SIMU_B200_OK;
-    scale_effects_kernel<<<(unsigned)((mc + 255) / 256), 256, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, d_comp, d_spow, ncomp,
-                                                                              op, d_bad);
-    ctx->launches++;
-    return ctx_cuda(ctx, cudaGetLastError(), "scale_effects_kernel launch");
+    return launch_scale_effects_on(ctx, ctx->stream, d_freq, d_x1, d_x2, mc, d_comp, d_spow, ncomp, op, d_bad, 0);
 }
 
 int launch_liability_split(simu_b200_ctx *ctx, const double *d_pheno, int64_t n, int64_t max_ncon, uint8_t *d_is_case)

@@ -1,5 +1,6 @@
-"""The experimental one-pass entry point simu_b200_find_freq_pheno (counts + effect scaling +
-FAST lookups in ONE kernel, GROUP4 panels) against the calls it replaces:
+"""simu_b200_find_freq_pheno (counts + effect scaling + FAST lookups behind one call, GROUP4 panels)
+-- both implementations: "overlap" (default: the standard kernels as a chunked two-stream pipeline) and
+"onepass" (the experimental single persistent kernel) -- against the calls it replaces:
     find_freq -> scale_effects -> find_pheno
 counts and frequencies bit-exact, scaled effects within 1e-14, phenotypes within the FAST
 tolerance of the bit-exact EXACT mode (which the parity tests pin against the oracle)."""
@@ -14,8 +15,16 @@ CASES = [(4096, 64, False), (4096, 64, True), (5003, 257, True), (10000, 1000, F
          (20000, 3000, False), (1, 5, False), (7, 1, True), (250001, 130, False), (500000, 80, False), (40000, 5000, True)]
 
 
+@pytest.fixture(params=["overlap", "overlap-1MB-chunks", "onepass"])
+def impl(request, monkeypatch):
+    monkeypatch.setenv("SIMU_B200_FUSED_IMPL", "onepass" if request.param == "onepass" else "overlap")
+    if request.param == "overlap-1MB-chunks":
+        monkeypatch.setenv("SIMU_B200_OVERLAP_MB", "1")       # many chunks even on the small cases
+    return request.param
+
+
 @pytest.mark.parametrize("n,mc,k2", CASES)
-def test_one_pass_matches_the_three_calls(n, mc, k2):
+def test_one_call_matches_the_three_calls(n, mc, k2, impl):
     rng = np.random.default_rng(n + mc)
     r1 = rng.standard_normal(mc)
     r2 = rng.standard_normal(mc) if k2 else None
@@ -37,7 +46,7 @@ def test_one_pass_matches_the_three_calls(n, mc, k2):
                 assert np.max(np.abs(y2 - e2)) <= 1e-5 * np.max(np.abs(e2))
 
 
-def test_one_pass_reports_zero_het_and_needs_group4():
+def test_one_call_reports_zero_het_and_needs_group4(impl):
     n, mc = 3000, 40
     with capi.Context(n) as ctx:
         ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
