@@ -294,6 +294,19 @@ def run_ours(args, w):
     d_is_case = torch.empty(n, dtype=torch.uint8, device=dev)
     max_ncon = n - int(np.floor(np.float32(0.1) * np.float32(n)))        # --k 0.1 (source.cc:1038-1039)
     mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
+    # the one exchange step: one-shot all-reduce over NVLink peer memory (simu_b200_peer_*), NCCL as the fallback
+    allreduce = "nccl"
+    if world > 1 and args.allreduce == "peer":
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.peer_init(rank, world, k * n))
+            ctx.peer_connect(handles)
+            ok = torch.ones(1, device=dev)
+        except capi.SimuB200Error as e:
+            print(f"rank {rank}: peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        allreduce = "peer" if ok.item() > 0 else "nccl"
     fused = args.fused and g4 and mode == capi.MODE_FAST
     if fused:      # one pass: the raw draws go in, the kernel scales them by het^-1/2 (--gcta-sigma) itself
         r1, r2 = _raw_effects(w, rank)
@@ -315,8 +328,11 @@ def run_ours(args, w):
             ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
             ctx.find_pheno_dev(rows_ptr, mc, d_freq.data_ptr(), d_x1.data_ptr(), d_x2.data_ptr() if k == 2 else 0,
                                d_y[0].data_ptr(), d_y[1].data_ptr() if k == 2 else 0, mode)
-        if world > 1:
-            dist.all_reduce(d_y)                     # the path's one exchange step
+        if world > 1:                                # the path's one exchange step
+            if allreduce == "peer":
+                ctx.peer_allreduce_dev(d_y.data_ptr(), k * n)
+            else:
+                dist.all_reduce(d_y)
         for t in range(k):
             ctx.sumsq_dev(d_y[t].data_ptr(), n, d_misc[t].data_ptr())
             ctx.heritability_dev(HSQ[t], d_y[t].data_ptr(), n, d_noise[t].data_ptr(), d_misc[t].data_ptr(),
@@ -477,7 +493,7 @@ def run_ours(args, w):
                        "hbm_panel": ("causal rows only, compact, GROUP4 (4 rows sample-interleaved)" if g4 else
                                      "whole .bed slice row-major + causal row list"),
                        "l2": f"inputs larger than L2 ({mc * B / 1e6:.0f} MB of causal rows per pass, 126 MB L2)",
-                       "parallelism": f"snp-shard x{world}, 1 all-reduce" if world > 1 else "single GPU"},
+                       "parallelism": f"snp-shard x{world}, 1 all-reduce ({allreduce})" if world > 1 else "single GPU"},
             "bed_gbs": 2 * mc * B * world / (ms_step * 1e-3) / 1e9,
             "roofline": roof, "roofline_counts": counts_roof, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
@@ -531,6 +547,8 @@ def main():
                          "SIMU_B200_FUSED_IMPL=onepass selects the experimental single-kernel version)")
     ap.add_argument("--cc-sort", action="store_true",
                     help="--cc workloads: full liability argsort (needed when --ncas/--ncon select a subset) instead of the split")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the partial-phenotype exchange as a one-shot all-reduce over NVLink peer memory, or NCCL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
     args = ap.parse_args()

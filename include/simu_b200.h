@@ -271,6 +271,22 @@ SIMU_B200_API int simu_b200_scale_effects_dev(simu_b200_ctx *ctx, int op, const 
                                               double *d_effect2, int64_t mc, const int32_t *d_component,
                                               const double *d_s_pow, int num_components, uint64_t *d_bad_index);
 
+/* ------------------------------------------------ multi-GPU exchange (one process per GPU)
+ * The path's one collective -- the sum of the per-rank partial N x K phenotypes -- as
+ * a one-shot all-reduce over NVLink peer memory: every rank publishes its partial in a symmetric
+ * buffer, flags the peers, and sums all partials straight out of the peers' HBM in rank order
+ * (identical bits on all ranks).  Latency-bound (0.8-8 MB): one cooperative kernel instead of a NCCL call.
+ *   peer_init      allocates the symmetric buffer for `count` doubles (K * N) and returns its 64-byte
+ *                  CUDA IPC handle, which the caller exchanges between the ranks by any means
+ *                  (torch.distributed.all_gather_object, MPI, a file ...);
+ *   peer_connect   maps the other ranks' buffers (handles: world x 64 bytes in rank order);
+ *   peer_allreduce_dev  d_y[i] = sum over ranks of d_y[i], in place, asynchronous on the context
+ *                  stream; every rank must call it the same number of times. */
+SIMU_B200_API int simu_b200_peer_init(simu_b200_ctx *ctx, int rank, int world, int64_t count, void *handle_out);
+SIMU_B200_API int simu_b200_peer_connect(simu_b200_ctx *ctx, const void *handles);
+SIMU_B200_API int simu_b200_peer_allreduce_dev(simu_b200_ctx *ctx, double *d_y, int64_t count);
+SIMU_B200_API void simu_b200_peer_close(simu_b200_ctx *ctx);
+
 /* Device time in milliseconds of the last find_freq / find_pheno call on this
  * context, measured with CUDA events on the launching stream (kernels only;
  * 0 if none).  which: 0 = find_freq, 1 = find_pheno. */

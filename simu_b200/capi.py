@@ -62,6 +62,10 @@ SIGNATURES = {
     "simu_b200_sumsq_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "simu_b200_heritability_dev": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp, _vp]),
     "simu_b200_liability_order_dev": (_i32, [_vp, _vp, _i64, _vp]),
+    "simu_b200_peer_init": (_i32, [_vp, _i32, _i32, _i64, _vp]),
+    "simu_b200_peer_connect": (_i32, [_vp, _vp]),
+    "simu_b200_peer_allreduce_dev": (_i32, [_vp, _vp, _i64]),
+    "simu_b200_peer_close": (None, [_vp]),
     "simu_b200_last_kernel_ms": (_i32, [_vp, _i32, C.POINTER(C.c_float)]),
     "simu_b200_profile_enable": (_i32, [_vp, _i32]),
     "simu_b200_profile_read": (_i32, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
@@ -319,6 +323,20 @@ class Context:
         self._check(self.lib.simu_b200_find_freq_pheno_dev(self.h, mc, v(d_raw1), v(d_raw2), scale_op, v(d_comp), v(d_spow),
                                                            ncomp, v(d_counts), v(d_freq), v(d_x1), v(d_x2), v(d_y1),
                                                            v(d_y2), v(d_bad)))
+
+    # -- multi-GPU exchange over NVLink peer memory --------------------------------
+    def peer_init(self, rank: int, world: int, count: int) -> bytes:
+        """-> the 64-byte IPC handle of this rank's symmetric buffer (exchange it, then peer_connect)."""
+        h = C.create_string_buffer(64)
+        self._check(self.lib.simu_b200_peer_init(self.h, rank, world, count, h))
+        return h.raw
+
+    def peer_connect(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        self._check(self.lib.simu_b200_peer_connect(self.h, C.c_char_p(blob)))
+
+    def peer_allreduce_dev(self, d_y, count: int):
+        self._check(self.lib.simu_b200_peer_allreduce_dev(self.h, C.c_void_p(d_y), count))
 
     def sumsq_dev(self, d_y, n, d_out):
         self._check(self.lib.simu_b200_sumsq_dev(self.h, C.c_void_p(d_y), n, C.c_void_p(d_out)))

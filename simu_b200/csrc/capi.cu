@@ -144,6 +144,7 @@ int simu_b200_open(simu_b200_ctx **out, int device, int64_t num_samples)
 void simu_b200_close(simu_b200_ctx *ctx)
 {
     if (!ctx) return;
+    simu_b200_peer_close(ctx);
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->panel) cudaFree(ctx->panel);

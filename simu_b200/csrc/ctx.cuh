@@ -14,6 +14,8 @@
 #define SIMU_STAGE_BYTES (64u << 20)  // pinned staging chunk (2 of them)
 #define SIMU_NUM_SMS_DEFAULT 148
 
+struct simu_b200_peer;
+
 struct simu_b200_ctx {
     int device = 0;
     int num_sms = SIMU_NUM_SMS_DEFAULT;
@@ -55,6 +57,7 @@ struct simu_b200_ctx {
     float last_ms[2] = {0.f, 0.f};
     std::vector<cudaEvent_t> chunk_events;   // overlap pipeline of find_freq_pheno
     cudaStream_t aux_stream = nullptr;
+    simu_b200_peer *peer = nullptr;          // multi-GPU exchange over NVLink peer memory (peer.cu)
     std::string err;
 };
 

@@ -420,6 +420,25 @@ def test_liability_threshold_labels_agree_with_oracle():
     assert (np.count_nonzero(lab == 2), np.count_nonzero(lab == 1)) == (300, 700)
 
 
+def test_peer_allreduce_single_rank_is_the_identity():
+    """World size 1 of the NVLink peer-memory all-reduce (2+ ranks: tools/peer_allreduce_check.py under torchrun)."""
+    import torch
+    n = 100_003
+    with capi.Context(n) as ctx:
+        h = ctx.peer_init(0, 1, 2 * n)
+        assert len(h) == 64
+        ctx.peer_connect([h])
+        y = torch.randn(2 * n, dtype=torch.float64, device="cuda")
+        want = y.clone()
+        for _ in range(5):
+            ctx.peer_allreduce_dev(y.data_ptr(), 2 * n)
+        ctx.sync()
+        torch.cuda.synchronize()
+        assert torch.equal(y, want)
+        with pytest.raises(capi.SimuB200Error):
+            ctx.peer_allreduce_dev(y.data_ptr(), n)            # count differs from peer_init
+
+
 # ------------------------------------------------------- staging from .bed
 
 @LAYOUTS
