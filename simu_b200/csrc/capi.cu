@@ -316,14 +316,6 @@ static int check_rows(simu_b200_ctx *ctx, const char *who, int64_t first, int64_
     return SIMU_B200_OK;
 }
 
-// make the compute stream wait for everything queued on the copy stream
-static int join_copy_stream(simu_b200_ctx *ctx)
-{
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    return SIMU_B200_OK;
-}
-
 // make the copy stream wait for everything queued on the compute stream (panel memset etc.)
 static int fork_copy_stream(simu_b200_ctx *ctx)
 {

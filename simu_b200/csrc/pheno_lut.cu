@@ -8,7 +8,15 @@
 // four SNP rows are combined into one byte index e and one table of 256
 // entries: one shared-memory load + one add per FOUR genotypes per trait.
 //
-// Layout of one step (64 causal rows x 4096 samples) in a CTA:
+// This file holds, in this order:
+//   lut_build_kernel        the tables (FP64 -> FP32), once per run
+//   pheno_lut_kernel        ROWS panels (row-major, optional row list): the layout described below
+//   pheno_lut_g4_kernel     GROUP4 panels (the product layout): the byte in HBM IS the table index, so the
+//                           bit transposition and three of the four row-word loads disappear
+//   pheno_fused_g4_kernel   EXPERIMENTAL counts + lookups in one persistent kernel
+//   lut_reduce_kernel, the launchers, and find_freq_pheno built from the standard kernels
+//
+// Layout of one step (64 causal rows x 4096 samples) in a CTA (ROWS panels):
 //   * tile: 64 rows x 1024 B in shared memory, filled by one TMA bulk copy
 //     (cp.async.bulk) per row issued by 8 producer warps (8 rows each);
 //   * table: 16 groups (4 rows each) x 256 entries, 32 KB, precomputed once
