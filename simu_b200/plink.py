@@ -166,6 +166,35 @@ class PlinkFiles:
             dst += local.size
 
 
+# ------------------------------------------------------------- GROUP4 layout (host restatement)
+
+def interleave_group4(packed_rows: np.ndarray, n_samples: int, group_stride: int | None = None) -> np.ndarray:
+    """Packed .bed rows [M, >=ceil(N/4)] -> the GROUP4 panel image [ceil(M/4), group_stride]:
+    byte i of group g = the 2-bit fields of sample i for rows 4g..4g+3, row 4g in bits 0-1
+    (include/simu_b200.h, SIMU_B200_LAYOUT_GROUP4).  What interleave_kernel (csrc/stage.cu)
+    produces on the device; rows beyond M read as 00."""
+    m = packed_rows.shape[0]
+    if group_stride is None:
+        group_stride = (n_samples + 127) // 128 * 128
+    i = np.arange(n_samples)
+    out = np.zeros(((m + 3) // 4, group_stride), dtype=np.uint8)
+    for r in range(m):
+        field = (packed_rows[r, i // 4] >> (2 * (i % 4))) & 3
+        out[r // 4, :n_samples] |= (field << (2 * (r % 4))).astype(np.uint8)
+    return out
+
+
+def deinterleave_group4(panel: np.ndarray, n_rows: int, n_samples: int) -> np.ndarray:
+    """The inverse: GROUP4 panel image -> packed .bed rows [n_rows, ceil(N/4)] (padding bits 00)."""
+    B = row_bytes(n_samples)
+    i = np.arange(n_samples)
+    out = np.zeros((n_rows, B), dtype=np.uint8)
+    for r in range(n_rows):
+        field = (panel[r // 4, :n_samples] >> (2 * (r % 4))) & 3
+        np.bitwise_or.at(out[r], i // 4, (field << (2 * (i % 4))).astype(np.uint8))
+    return out
+
+
 # ------------------------------------------------------------- fixture writers
 
 def write_bed(path: str, packed_rows: np.ndarray, n_samples: int) -> None:

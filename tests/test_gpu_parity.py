@@ -233,6 +233,7 @@ def test_group4_byte_is_the_table_index():
     n, m = 300, 8
     rows = _panel(n, m)
     codes = np.stack([(rows[j, np.arange(n) // 4] >> (2 * (np.arange(n) % 4))) & 3 for j in range(m)])
+    host_image = plink.interleave_group4(rows, n)            # the host restatement of the layout
     with capi.Context(n) as ctx:
         ctx.panel_alloc(m, capi.LAYOUT_GROUP4)
         ctx.panel_put_rows(0, rows)
@@ -246,6 +247,7 @@ def test_group4_byte_is_the_table_index():
     for g in range(2):
         want = codes[4 * g] | (codes[4 * g + 1] << 2) | (codes[4 * g + 2] << 4) | (codes[4 * g + 3] << 6)
         assert np.array_equal(raw[g, :n], want.astype(np.uint8))
+    assert np.array_equal(raw, host_image)
 
 
 def test_group4_rejects_row_lists():
