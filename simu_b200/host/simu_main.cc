@@ -17,6 +17,7 @@
 #include <limits>
 #include <memory>
 #include <sstream>
+#include <thread>
 
 #include <sys/stat.h>
 
@@ -459,20 +460,58 @@ void find_causals(const SimuOptions &o, Mt19937 &rng, Logger &log, const PlinkFi
 }
 
 // ---------------------------------------------------------------- the GPU session
+//
+// One context per GPU.  SIMU_B200_DEVICE=n (default 0) selects a single GPU; SIMU_B200_DEVICES=all or a
+// list "0,1,2,3" shards the path by SNP over several GPUs of the box: the ascending causal
+// list is cut into contiguous slices balanced by causal-row count, every GPU stages and processes its
+// slice from its own host thread, frequencies are concatenated and the partial phenotypes summed on the
+// host in device order (deterministic; with more than one GPU the sum order differs from the reference's,
+// so EXACT mode is then tolerance-matched, not bit-identical).
 
 struct Gpu {
-    simu_b200_ctx *ctx = nullptr;
-    std::vector<int> causal;      // ascending variant indices staged in the panel, in order
-    ~Gpu() { if (ctx) simu_b200_close(ctx); }
-    void check(int rc) const
+    std::vector<simu_b200_ctx *> ctxs;
+    simu_b200_ctx *ctx = nullptr;     // ctxs[0]: the O(N) reductions and the threshold run there
+    std::vector<int> causal;          // ascending variant indices staged in the panels, in order
+    std::vector<size_t> lo, hi;       // slice [lo[d], hi[d]) of `causal` owned by GPU d
+    ~Gpu() { for (simu_b200_ctx *c : ctxs) if (c) simu_b200_close(c); }
+    void check(int rc) const { check(ctx, rc); }
+    static void check(const simu_b200_ctx *c, int rc)
     {
-        if (rc != SIMU_B200_OK) throw std::runtime_error(simu_b200_last_error(ctx));
+        if (rc != SIMU_B200_OK) throw std::runtime_error(simu_b200_last_error(c));
     }
     void open(int num_samples)
     {
-        const char *d = getenv("SIMU_B200_DEVICE");
-        if (simu_b200_open(&ctx, d ? atoi(d) : 0, num_samples) != SIMU_B200_OK)
-            throw std::runtime_error(std::string("ERROR: ") + simu_b200_last_error(nullptr));
+        std::vector<int> devices;
+        if (const char *all = getenv("SIMU_B200_DEVICES")) {
+            if (std::string(all) == "all") {
+                int n = 0;
+                if (simu_b200_device_count(&n) != SIMU_B200_OK) throw std::runtime_error(std::string("ERROR: ") + simu_b200_last_error(nullptr));
+                for (int d = 0; d < n; d++) devices.push_back(d);
+            } else {
+                std::stringstream ss(all);
+                std::string tok;
+                while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+            }
+        }
+        if (devices.empty()) { const char *d = getenv("SIMU_B200_DEVICE"); devices.push_back(d ? atoi(d) : 0); }
+        for (int d : devices) {
+            simu_b200_ctx *c = nullptr;
+            if (simu_b200_open(&c, d, num_samples) != SIMU_B200_OK)
+                throw std::runtime_error(std::string("ERROR: ") + simu_b200_last_error(nullptr));
+            ctxs.push_back(c);
+        }
+        ctx = ctxs[0];
+    }
+    // run fn(d) for every GPU, each on its own host thread; rethrow the first failure
+    template <typename F> void for_each_gpu(F fn) const
+    {
+        if (ctxs.size() == 1) { fn((size_t)0); return; }
+        std::vector<std::thread> pool;
+        std::vector<std::string> errors(ctxs.size());
+        for (size_t d = 0; d < ctxs.size(); d++)
+            pool.emplace_back([&, d] { try { fn(d); } catch (std::exception &e) { errors[d] = e.what(); if (errors[d].empty()) errors[d] = "error"; } });
+        for (auto &t : pool) t.join();
+        for (const auto &e : errors) if (!e.empty()) throw std::runtime_error(e);
     }
     // stage the causal rows of every bfile, in variant order (the rows pio_next_row would read)
     void stage(const SimuOptions &o, const std::vector<int> &comp, const PlinkFiles &pio)
@@ -486,20 +525,30 @@ struct Gpu {
         causal.clear();
         for (int v = 0; v < o.num_variants; v++)
             if (comp[v] != -1) causal.push_back(v);
-        // compact causal panel (only the rows pio_next_row would read), sample-interleaved in groups of four
-        // rows so that find_pheno's FAST kernel reads its table index directly
-        check(simu_b200_panel_alloc_layout(ctx, std::max<size_t>(1, causal.size()), SIMU_B200_LAYOUT_GROUP4));
-        size_t pos = 0;
-        int64_t dst = 0;
-        for (size_t f = 0; f < pio.num_files(); f++) {
-            const int lo = pio.offset(f), hi = lo + pio.file(f).num_loci();
-            std::vector<int64_t> local;
-            while (pos < causal.size() && causal[pos] < hi) local.push_back(causal[pos++] - lo);
-            if (local.empty()) continue;
-            check(simu_b200_panel_load_bed(ctx, (pio.file(f).prefix + ".bed").c_str(), pio.file(f).num_loci(), local.data(),
-                                           (int64_t)local.size(), dst));
-            dst += (int64_t)local.size();
+        const size_t D = ctxs.size(), mc = causal.size();
+        lo.assign(D, 0); hi.assign(D, 0);
+        for (size_t d = 0, at = 0; d < D; d++) {          // contiguous slices, balanced by causal-row count
+            lo[d] = at;
+            at += mc / D + (d < mc % D ? 1 : 0);
+            hi[d] = at;
         }
+        for_each_gpu([&](size_t d) {
+            simu_b200_ctx *c = ctxs[d];
+            // compact causal panel (only the rows pio_next_row would read), sample-interleaved in groups of four
+            // rows so that find_pheno's FAST kernel reads its table index directly
+            check(c, simu_b200_panel_alloc_layout(c, std::max<size_t>(1, hi[d] - lo[d]), SIMU_B200_LAYOUT_GROUP4));
+            size_t pos = lo[d];
+            int64_t dst = 0;
+            for (size_t f = 0; f < pio.num_files() && pos < hi[d]; f++) {
+                const int flo = pio.offset(f), fhi = flo + pio.file(f).num_loci();
+                std::vector<int64_t> local;
+                while (pos < hi[d] && causal[pos] < fhi) local.push_back(causal[pos++] - flo);
+                if (local.empty()) continue;
+                check(c, simu_b200_panel_load_bed(c, (pio.file(f).prefix + ".bed").c_str(), pio.file(f).num_loci(), local.data(),
+                                                  (int64_t)local.size(), dst));
+                dst += (int64_t)local.size();
+            }
+        });
     }
 };
 
@@ -510,7 +559,11 @@ void find_freq(const SimuOptions &o, const std::vector<int> &comp, const PlinkFi
     gpu.stage(o, comp, pio);
     if (gpu.causal.empty()) return;
     std::vector<double> f(gpu.causal.size());
-    gpu.check(simu_b200_find_freq(gpu.ctx, nullptr, (int64_t)gpu.causal.size(), nullptr, f.data()));
+    gpu.for_each_gpu([&](size_t d) {
+        if (gpu.hi[d] > gpu.lo[d])
+            Gpu::check(gpu.ctxs[d], simu_b200_find_freq(gpu.ctxs[d], nullptr, (int64_t)(gpu.hi[d] - gpu.lo[d]), nullptr,
+                                                        f.data() + gpu.lo[d]));
+    });
     for (size_t j = 0; j < gpu.causal.size(); j++) (*freq_vec)[gpu.causal[j]] = f[j];
 }
 
@@ -530,8 +583,26 @@ void find_pheno(const SimuOptions &o, const std::vector<double> &freq_vec, const
     if (bivariate) pheno2->assign(o.num_samples, 0.0);
     const char *m = getenv("SIMU_B200_MODE");
     const int mode = (m && std::string(m) == "exact") ? SIMU_B200_MODE_EXACT : SIMU_B200_MODE_FAST;
-    gpu.check(simu_b200_find_pheno(gpu.ctx, nullptr, (int64_t)mc, f.data(), x1.data(), bivariate ? x2.data() : nullptr,
-                                   pheno1->data(), bivariate ? pheno2->data() : nullptr, mode));
+    const size_t D = gpu.ctxs.size();
+    if (D == 1) {
+        gpu.check(simu_b200_find_pheno(gpu.ctx, nullptr, (int64_t)mc, f.data(), x1.data(), bivariate ? x2.data() : nullptr,
+                                       pheno1->data(), bivariate ? pheno2->data() : nullptr, mode));
+        return;
+    }
+    // one partial N x K phenotype per GPU, summed in device order (the path's one exchange step)
+    std::vector<std::vector<double>> p1(D, std::vector<double>(o.num_samples, 0.0)), p2(D);
+    if (bivariate) for (auto &v : p2) v.assign(o.num_samples, 0.0);
+    gpu.for_each_gpu([&](size_t d) {
+        const size_t l = gpu.lo[d], n = gpu.hi[d] - l;
+        Gpu::check(gpu.ctxs[d], simu_b200_find_pheno(gpu.ctxs[d], nullptr, (int64_t)n, f.data() + l, x1.data() + l,
+                                                     bivariate ? x2.data() + l : nullptr, p1[d].data(),
+                                                     bivariate ? p2[d].data() : nullptr, mode));
+    });
+    for (size_t d = 0; d < D; d++)
+        for (int i = 0; i < o.num_samples; i++) {
+            (*pheno1)[i] += p1[d][i];
+            if (bivariate) (*pheno2)[i] += p2[d][i];
+        }
 }
 
 void apply_heritability(float hsq, Mt19937 &rng, Gpu &gpu, std::vector<double> *pheno, std::vector<double> *effect)

@@ -26,8 +26,10 @@ CLI = os.path.join(ROOT, "simu_b200", "bin", "simu_b200")
 F32 = np.float32
 
 
-def run(args, cwd, mode="fast"):
+def run(args, cwd, mode="fast", devices=None):
     env = dict(os.environ, SIMU_B200_MODE=mode)
+    if devices:
+        env["SIMU_B200_DEVICES"] = devices
     p = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     return p.stdout
@@ -173,6 +175,36 @@ def test_bfile_chr_concatenation(tmp_path):
     _, body = read_table(tmp_path / "chr.1.causals")
     chrom = lambda v: "1" if v < 40 else ("2" if v < 65 else "3")     # noqa: E731
     assert [(r[0], r[1]) for r in body] == [(f"rs{v}", chrom(v)) for v in causal]
+
+
+@pytest.mark.parametrize("devices", ["0,0,0", "all"])
+def test_snp_sharding_over_several_contexts(tmp_path, devices):
+    """SIMU_B200_DEVICES: the causal list cut into contiguous slices, one context (and host thread) per
+    slice, frequencies concatenated, partial phenotypes summed -- here three contexts on GPU 0 (runs on
+    a one-GPU box) and every GPU of the box; slices cross the bfile boundaries of --bfile-chr."""
+    n = 701
+    sizes = {"1": 40, "2": 25, "3": 35}
+    rows = oracle.synth_rows(20240901, 0, sum(sizes.values()), n)
+    off = 0
+    for lab, sz in sizes.items():
+        plink.write_fileset(str(tmp_path / f"c{lab}"), rows[off:off + sz], n, chromosome=int(lab), first_index=off)
+        off += sz
+    args = ["--bfile-chr", "c@", "--chr-labels", "1", "2", "3", "--qt", "--num-traits", "2", "--rg", "0.3", "--gcta-sigma",
+            "--causal-pi", "0.47", "--hsq", "0.6", "0.4", "--seed", "5"]
+    for mode in ("exact", "fast"):
+        run(args + ["--out", f"one_{mode}"], tmp_path, mode)
+        run(args + ["--out", f"many_{mode}"], tmp_path, mode, devices=devices)
+        for ext in (".pheno", ".1.causals", ".2.causals"):
+            h1, b1 = read_table(tmp_path / f"one_{mode}{ext}")
+            h2, b2 = read_table(tmp_path / f"many_{mode}{ext}")
+            assert h1 == h2 and len(b1) == len(b2)
+            ncol = len(h1)
+            first_num = 2 if ext == ".pheno" else 5
+            assert [r[:first_num] for r in b1] == [r[:first_num] for r in b2]
+            for c in range(first_num, ncol):
+                assert close([r[c] for r in b2], [r[c] for r in b1], rtol=1e-5 if mode == "fast" else 1e-12)
+    # more contexts than causal variants: empty slices are fine
+    run(["--bfile", "c1", "--qt", "--causal-n", "2", "--seed", "1", "--out", "tiny"], tmp_path, "fast", devices="0,0,0")
 
 
 def test_causal_regions_and_components(fileset):
