@@ -10,14 +10,45 @@
 //   FileText    a whole text file in memory, tokenised in place (no per-field std::string).
 #pragma once
 
+#include <algorithm>
 #include <charconv>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <vector>
 
 namespace simu {
+
+// The same operator<< set into a growing memory buffer: worker threads format slices of a big table
+// (.causals of an 11M-variant run) in parallel, the owner writes the slices out in order.
+class MemWriter {
+public:
+    MemWriter &operator<<(std::string_view s) { buf_.append(s.data(), s.size()); return *this; }
+    MemWriter &operator<<(const std::string &s) { buf_.append(s); return *this; }
+    MemWriter &operator<<(const char *s) { buf_.append(s); return *this; }
+    MemWriter &operator<<(char c) { buf_.push_back(c); return *this; }
+    MemWriter &operator<<(double v)       // == ostream << double at precision 6 == printf("%g")
+    {
+        char tmp[40];
+        buf_.append(tmp, (size_t)(std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::general, 6).ptr - tmp));
+        return *this;
+    }
+    MemWriter &operator<<(long long v)
+    {
+        char tmp[24];
+        buf_.append(tmp, (size_t)(std::to_chars(tmp, tmp + sizeof(tmp), v).ptr - tmp));
+        return *this;
+    }
+    MemWriter &operator<<(int v) { return *this << (long long)v; }
+    const std::string &str() const { return buf_; }
+    void reserve(size_t n) { buf_.reserve(n); }
+
+private:
+    std::string buf_;
+};
 
 class TextWriter {
 public:
@@ -99,6 +130,33 @@ public:
         pos_ = (size_t)(q - base) + 1;
         return true;
     }
+    char *begin() { return data_.empty() ? nullptr : &data_[0]; }
+    size_t size() const { return data_.size(); }
+    // cut the text into `parts` pieces that end on line boundaries: piece p = [cuts[p], cuts[p+1])
+    std::vector<size_t> cut_at_lines(int parts) const
+    {
+        std::vector<size_t> cuts(1, 0);
+        for (int p = 1; p < parts; p++) {
+            size_t at = data_.size() * (size_t)p / (size_t)parts;
+            if (at < cuts.back()) at = cuts.back();
+            const void *nl = at < data_.size() ? memchr(data_.data() + at, '\n', data_.size() - at) : nullptr;
+            cuts.push_back(nl ? (size_t)((const char *)nl - data_.data()) + 1 : data_.size());
+        }
+        cuts.push_back(data_.size());
+        return cuts;
+    }
+    // next line of [*pos, end) (without '\n') into [*b, *e); false when the piece is exhausted
+    bool next_line_in(size_t *pos, size_t end, char **b, char **e)
+    {
+        if (*pos >= end) return false;
+        char *base = &data_[0];
+        char *p = base + *pos, *stop = base + end;
+        char *q = (char *)memchr(p, '\n', (size_t)(stop - p));
+        if (!q) q = stop;
+        *b = p; *e = q;
+        *pos = (size_t)(q - base) + 1;
+        return true;
+    }
     // split [b, e) into at most max_fields views; returns the number of fields found (may exceed max_fields)
     static int split(char *b, char *e, std::string_view *out, int max_fields)
     {
@@ -119,6 +177,23 @@ private:
     size_t pos_ = 0;
     bool ok_ = false;
 };
+
+// host threads for the text stages (SIMU_B200_IO_THREADS, default min(8, cores))
+inline int text_threads()
+{
+    if (const char *e = getenv("SIMU_B200_IO_THREADS")) return std::max(1, atoi(e));
+    return (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+}
+
+// run fn(t) for t in [0, n) on n threads (n == 1: inline)
+template <typename F> inline void parallel_for_threads(int n, F fn)
+{
+    if (n <= 1) { fn(0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n; t++) pool.emplace_back(fn, t);
+    fn(0);
+    for (auto &th : pool) th.join();
+}
 
 // complete-token numeric parses (strtoll / strtod semantics of the reference's parsers, which
 // require the whole field to be consumed: bim_parse.c:112-175)

@@ -54,29 +54,55 @@ inline std::vector<std::string> split_blank(const std::string &line)
     return out;
 }
 
+// One .bim line into *l.  Returns 0 for a blank line, 1 for a record, -1 for a malformed line.
+inline int parse_bim_line(char *b, char *e, Locus *l)
+{
+    std::string_view t[6];
+    const int n = FileText::split(b, e, t, 6);
+    if (n == 0) return 0;
+    if (n > 6) return -1;
+    long long v;
+    double d;
+    // rows with fewer than six fields are kept with defaults, as libplinkio's new_row does
+    if (n > 0) { if (!full_long(t[0], &v)) return -1; l->chromosome = (unsigned char)v; }
+    if (n > 1) l->name.assign(t[1]);
+    if (n > 2) { if (!full_double(t[2], &d)) return -1; l->position = (float)d; }
+    if (n > 3) { if (!full_long(t[3], &v)) return -1; l->bp_position = v; }
+    if (n > 4) l->allele1.assign(t[4]);
+    if (n > 5) l->allele2.assign(t[5]);
+    return 1;
+}
+
 inline bool parse_bim_file(const std::string &path, std::vector<Locus> *loci)
 {
     FileText f(path);                      // whole file in memory, fields tokenised in place
     if (!f.ok()) return false;
-    char *b, *e;
-    std::string_view t[6];
-    loci->reserve(loci->size() + f.count_lines());
-    while (f.next_line(&b, &e)) {
-        const int n = FileText::split(b, e, t, 6);
-        if (n == 0) continue;
-        if (n > 6) return false;
-        Locus l;
-        long long v;
-        double d;
-        // rows with fewer than six fields are kept with defaults, as libplinkio's new_row does
-        if (n > 0) { if (!full_long(t[0], &v)) return false; l.chromosome = (unsigned char)v; }
-        if (n > 1) l.name.assign(t[1]);
-        if (n > 2) { if (!full_double(t[2], &d)) return false; l.position = (float)d; }
-        if (n > 3) { if (!full_long(t[3], &v)) return false; l.bp_position = v; }
-        if (n > 4) l.allele1.assign(t[4]);
-        if (n > 5) l.allele2.assign(t[5]);
-        loci->push_back(std::move(l));
-    }
+    // big files: the text is cut at line boundaries and the pieces are parsed by several threads --
+    // pass 1 counts the records of each piece, pass 2 parses them straight into their final slots
+    const int parts = f.size() > (4u << 20) ? text_threads() : 1;
+    const std::vector<size_t> cuts = f.cut_at_lines(parts);
+    std::vector<size_t> count((size_t)parts, 0);
+    parallel_for_threads(parts, [&](int p) {
+        size_t pos = cuts[(size_t)p];
+        char *b, *e;
+        std::string_view one[1];
+        while (f.next_line_in(&pos, cuts[(size_t)p + 1], &b, &e))
+            if (FileText::split(b, e, one, 1) > 0) count[(size_t)p]++;
+    });
+    std::vector<size_t> first((size_t)parts + 1, loci->size());
+    for (int p = 0; p < parts; p++) first[(size_t)p + 1] = first[(size_t)p] + count[(size_t)p];
+    loci->resize(first[(size_t)parts]);
+    std::vector<char> bad((size_t)parts, 0);
+    parallel_for_threads(parts, [&](int p) {
+        size_t pos = cuts[(size_t)p], at = first[(size_t)p];
+        char *b, *e;
+        while (f.next_line_in(&pos, cuts[(size_t)p + 1], &b, &e)) {
+            const int rc = parse_bim_line(b, e, &(*loci)[at < loci->size() ? at : 0]);
+            if (rc < 0) { bad[(size_t)p] = 1; return; }
+            at += (size_t)rc;
+        }
+    });
+    for (char x : bad) if (x) return false;
     return true;
 }
 

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _build(src, out):
-    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", src, "-o", out], check=True, cwd=ROOT)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-pthread", src, "-o", out], check=True, cwd=ROOT)
 
 
 def test_textwriter_formats_like_ostream(tmp_path):
@@ -22,7 +22,14 @@ def test_textwriter_formats_like_ostream(tmp_path):
     assert "0 differences" in r.stdout
 
 
-@pytest.mark.parametrize("m,n", [(1, 1), (50_000, 3_000)])
+def test_threaded_bim_parse_equals_single_thread(tmp_path):
+    exe = str(tmp_path / "bim_parse_check")
+    _build("tests/helpers/bim_parse_check.cc", exe)
+    r = subprocess.run([exe, str(tmp_path / "big.bim")], capture_output=True, text=True)
+    assert r.returncode == 0 and "threaded == single: yes" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (50_000, 3_000), (300_000, 100)])      # the last one takes the threaded paths
 def test_parser_map_and_writers_match_iostream_restatement(tmp_path, m, n):
     exe = str(tmp_path / "host_io_bench")
     _build("tools/host_io_bench.cc", exe)
