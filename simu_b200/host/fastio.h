@@ -195,6 +195,29 @@ template <typename F> inline void parallel_for_threads(int n, F fn)
     for (auto &th : pool) th.join();
 }
 
+// Write `count` table rows: row(out, j) prints row j into `out` (a TextWriter or a MemWriter -- the same
+// operator<< set).  Beyond 200K rows the slices of 1M-row batches are formatted into memory by several
+// threads and written out in order; the file gets the same bytes either way.
+template <typename RowFn> inline void write_rows(TextWriter &file, size_t count, RowFn row)
+{
+    const int threads = count > 200000 ? text_threads() : 1;
+    if (threads == 1) {
+        for (size_t j = 0; j < count; j++) row(file, j);
+        return;
+    }
+    const size_t batch = (size_t)1 << 20;
+    for (size_t b0 = 0; b0 < count; b0 += batch) {
+        const size_t b1 = std::min(count, b0 + batch);
+        std::vector<MemWriter> parts((size_t)threads);
+        parallel_for_threads(threads, [&](int t) {
+            const size_t lo = b0 + (b1 - b0) * (size_t)t / (size_t)threads, hi = b0 + (b1 - b0) * (size_t)(t + 1) / (size_t)threads;
+            parts[(size_t)t].reserve((hi - lo) * 72);
+            for (size_t j = lo; j < hi; j++) row(parts[(size_t)t], j);
+        });
+        for (const MemWriter &m : parts) file << std::string_view(m.str());
+    }
+}
+
 // complete-token numeric parses (strtoll / strtod semantics of the reference's parsers, which
 // require the whole field to be consumed: bim_parse.c:112-175)
 inline bool full_long(std::string_view s, long long *v)

@@ -690,7 +690,11 @@ void save_causals_file(const SimuOptions &o, const std::string &path, const Plin
     file << "SNP\tCHR\tPOS\tA1\tA2\tFRQ";
     for (int i = 0; i < o.num_components; i++) file << "\tBETA_c" << (i + 1);
     file << "\n";
-    auto row = [&](auto &out, int v) {                  // one line, exactly as source.cc:1089-1105 prints it
+    std::vector<int> causal;
+    for (int v = 0; v < o.num_variants; v++)
+        if (comp[v] != -1) causal.push_back(v);
+    write_rows(file, causal.size(), [&](auto &out, size_t j) {          // one line, exactly as source.cc:1089-1105 prints it
+        const int v = causal[j];
         const Locus *l = pio.get_locus(v);
         double effect = effect_per_variant[v];
         if (o.norm_effect) effect *= sqrt(fabs(2 * freq[v] * (1 - freq[v])));
@@ -698,27 +702,7 @@ void save_causals_file(const SimuOptions &o, const std::string &path, const Plin
             << l->allele2 << "\t" << freq[v];
         for (int i = 0; i < o.num_components; i++) out << "\t" << ((i == comp[v]) ? effect : 0.0);
         out << "\n";
-    };
-    std::vector<int> causal;
-    for (int v = 0; v < o.num_variants; v++)
-        if (comp[v] != -1) causal.push_back(v);
-    const int threads = causal.size() > 200000 ? text_threads() : 1;
-    if (threads == 1) {
-        for (int v : causal) row(file, v);
-        return;
-    }
-    // millions of lines: slices are formatted into memory by several threads and written out in order
-    const size_t batch = (size_t)1 << 20;
-    for (size_t b0 = 0; b0 < causal.size(); b0 += batch) {
-        const size_t b1 = std::min(causal.size(), b0 + batch);
-        std::vector<MemWriter> parts((size_t)threads);
-        parallel_for_threads(threads, [&](int t) {
-            const size_t lo = b0 + (b1 - b0) * (size_t)t / (size_t)threads, hi = b0 + (b1 - b0) * (size_t)(t + 1) / (size_t)threads;
-            parts[(size_t)t].reserve((hi - lo) * 72);
-            for (size_t j = lo; j < hi; j++) row(parts[(size_t)t], causal[j]);
-        });
-        for (const MemWriter &m : parts) file << std::string_view(m.str());
-    }
+    });
 }
 
 }  // namespace

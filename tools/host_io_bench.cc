@@ -108,29 +108,13 @@ int main(int argc, char **argv)
     {
         TextWriter file(prefix + ".new.causals");
         file << "SNP\tCHR\tPOS\tA1\tA2\tFRQ\tBETA_c1\tBETA_c2\n";
-        auto row = [&](auto &out, long v) {
+        write_rows(file, (size_t)m, [&](auto &out, size_t v) {          // the product's writer path (fastio.h)
             const Locus &l = a[v];
             out << l.name << "\t" << static_cast<int>(l.chromosome) << "\t" << l.bp_position << "\t" << l.allele1 << "\t"
                 << l.allele2 << "\t" << freq[v];
             for (int c = 0; c < 2; c++) out << "\t" << ((c == (int)(v & 1)) ? eff[v] : 0.0);
             out << "\n";
-        };
-        const int threads = m > 200000 ? text_threads() : 1;      // as save_causals_file in simu_main.cc
-        if (threads == 1) {
-            for (long v = 0; v < m; v++) row(file, v);
-        } else {
-            const long batch = 1L << 20;
-            for (long b0 = 0; b0 < m; b0 += batch) {
-                const long b1 = std::min(m, b0 + batch);
-                std::vector<MemWriter> parts((size_t)threads);
-                parallel_for_threads(threads, [&](int t) {
-                    const long lo = b0 + (b1 - b0) * t / threads, hi = b0 + (b1 - b0) * (t + 1) / threads;
-                    parts[(size_t)t].reserve((size_t)(hi - lo) * 72);
-                    for (long v = lo; v < hi; v++) row(parts[(size_t)t], v);
-                });
-                for (const MemWriter &w : parts) file << std::string_view(w.str());
-            }
-        }
+        });
         TextWriter ph(prefix + ".new.pheno");
         ph << "FID\tIID\ttrait1\ttrait2\n";
         for (long i = 0; i < n; i++) ph << fam[i].fid << "\t" << fam[i].iid << "\t" << y1[i] << "\t" << y2[i] << "\n";
