@@ -133,6 +133,45 @@ inline bool parse_fam_file(const std::string &path, std::vector<Sample> *samples
     return true;
 }
 
+// Variant name -> index (PioFiles::snp_to_id_, source.cc:327-352).  The reference's std::map costs
+// O(log M) string compares per insert and lookup; this is a hash map keyed by views of the loci's own
+// names, in `shards` independent tables (shard = hash mod shards) that are filled by as many threads --
+// every thread hashes all names and inserts its own.  A duplicate is reported as the sequential build
+// would: the name whose SECOND occurrence comes first.
+class NameIndex {
+public:
+    // names[v] must stay alive and in place while the index is used
+    void build(const std::vector<std::string_view> &names)
+    {
+        const int shards = names.size() > 4000000 ? text_threads() : 1;     // below that one table is faster (0.3 s per 1M names)
+        maps_.assign((size_t)shards, {});
+        std::vector<long long> dup((size_t)shards, -1);
+        parallel_for_threads(shards, [&](int t) {
+            auto &m = maps_[(size_t)t];
+            m.reserve(names.size() / (size_t)shards * 2 + 16);
+            const std::hash<std::string_view> h;
+            for (size_t v = 0; v < names.size(); v++) {
+                if (shards > 1 && h(names[v]) % (size_t)shards != (size_t)t) continue;
+                if (!m.emplace(names[v], (int)v).second) { dup[(size_t)t] = (long long)v; return; }
+            }
+        });
+        long long first = -1;
+        for (long long d : dup) if (d >= 0 && (first < 0 || d < first)) first = d;
+        if (first >= 0) throw std::runtime_error("ERROR: duplicated variant name: " + std::string(names[(size_t)first]));
+    }
+    bool empty() const { return maps_.empty(); }
+    // -1 when absent
+    int find(std::string_view name) const
+    {
+        const auto &m = maps_[maps_.size() > 1 ? std::hash<std::string_view>()(name) % maps_.size() : 0];
+        auto it = m.find(name);
+        return it == m.end() ? -1 : it->second;
+    }
+
+private:
+    std::vector<std::unordered_map<std::string_view, int>> maps_;
+};
+
 // One bfile prefix (PioFile, source.cc:187-267).
 struct PlinkFile {
     std::string prefix;
@@ -188,29 +227,27 @@ public:
     {
         if (!snp_to_id_.empty())
             throw std::runtime_error("internal error - find_variant_index_map must be called once");
-        // hash map keyed by views of the loci's own names (the loci never move once all files are
-        // pushed); the reference's std::map costs O(log M) string compares per insert and lookup
-        snp_to_id_.reserve((size_t)num_variants_ * 2);
-        int v = 0;
+        // keyed by views of the loci's own names (the loci never move once all files are pushed)
+        std::vector<std::string_view> names;
+        names.reserve((size_t)num_variants_);
         for (const PlinkFile &f : files_)
-            for (const Locus &l : f.loci)
-                if (!snp_to_id_.emplace(std::string_view(l.name), v++).second)
-                    throw std::runtime_error("ERROR: duplicated variant name: " + l.name);
+            for (const Locus &l : f.loci) names.emplace_back(l.name);
+        snp_to_id_.build(names);
     }
     int get_locus_id(const std::string &name) const                                // source.cc:345-352
     {
-        auto it = snp_to_id_.find(std::string_view(name));
-        if (it == snp_to_id_.end())
+        const int id = snp_to_id_.empty() ? -1 : snp_to_id_.find(std::string_view(name));
+        if (id < 0)
             throw std::runtime_error("ERROR: locus with name " + name +
                                      " does not exist in the input; check your --bfile and/or --causal-variants, "
                                      "--causal-regions arguments");
-        return it->second;
+        return id;
     }
 
 private:
     std::vector<PlinkFile> files_;
     std::vector<int> offsets_;
-    std::unordered_map<std::string_view, int> snp_to_id_;
+    NameIndex snp_to_id_;
     int num_variants_ = 0;
 };
 

@@ -22,6 +22,13 @@ def test_textwriter_formats_like_ostream(tmp_path):
     assert "0 differences" in r.stdout
 
 
+def test_sharded_name_index_reports_duplicates_like_the_sequential_build(tmp_path):
+    exe = str(tmp_path / "name_index_check")
+    _build("tests/helpers/name_index_check.cc", exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
 def test_threaded_bim_parse_equals_single_thread(tmp_path):
     exe = str(tmp_path / "bim_parse_check")
     _build("tests/helpers/bim_parse_check.cc", exe)

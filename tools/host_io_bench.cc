@@ -84,11 +84,16 @@ int main(int argc, char **argv)
 
     // name map: build + look every 3rd name up (a --causal-variants file)
     t0 = clk::now();
-    std::unordered_map<std::string_view, int> hm;
-    hm.reserve(a.size() * 2);
-    for (size_t i = 0; i < a.size(); i++) ok &= hm.emplace(std::string_view(a[i].name), (int)i).second;
+    NameIndex index;                                   // the product's name index (plink_text.h)
+    {
+        std::vector<std::string_view> names;
+        names.reserve(a.size());
+        for (const Locus &l : a) names.emplace_back(l.name);
+        index.build(names);
+    }
     long sum_new = 0;
-    for (size_t i = 0; i < a.size(); i += 3) sum_new += hm.find(std::string_view(b[i].name))->second;
+    for (size_t i = 0; i < a.size(); i += 3) sum_new += index.find(std::string_view(b[i].name));
+    ok &= index.find("no_such_variant") == -1;
     const double t_map_new = secs(t0);
     t0 = clk::now();
     std::map<std::string, int> tm;
