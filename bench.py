@@ -492,6 +492,7 @@ def run_ours(args, w):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32-table/f64-accumulate" if mode == capi.MODE_FAST else "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": w["desc"], "n_samples": n, "panel_rows_per_gpu": m,
+                       "hbm_panel_rows_per_gpu": mc if g4 else m,
                        "n_causal_per_gpu": mc, "traits": k, "mode": args.mode,
                        "hbm_panel": ("causal rows only, compact, GROUP4 (4 rows sample-interleaved)" if g4 else
                                      "whole .bed slice row-major + causal row list"),
