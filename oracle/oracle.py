@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
                                        C.c_void_p, C.c_void_p]
         L.oracle_find_pheno.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_find_pheno_range.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_apply_heritability.argtypes = [C.c_float, C.c_void_p, C.c_size_t, C.c_void_p,
                                                 C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]
         L.oracle_apply_heritability.restype = C.c_double
@@ -65,6 +67,8 @@ def lib() -> C.CDLL:
                                            C.c_void_p, C.c_void_p]
         L.oracle_scale_effects.restype = C.c_long
         L.oracle_synth_rows.argtypes = [C.c_uint64, C.c_int64, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.oracle_synth_cols.argtypes = [C.c_uint64, C.c_int64, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                        C.c_void_p, C.c_size_t]
         _LIB = L
     return _LIB
 
@@ -203,7 +207,11 @@ def find_freq(rows: np.ndarray, n: int, row_index=None):
     return counts, freq
 
 
-def find_pheno(rows: np.ndarray, n: int, freq, x1, x2=None, row_index=None):
+def find_pheno(rows: np.ndarray, n: int, freq, x1, x2=None, row_index=None, threads: int = 1, samples=None):
+    """find_pheno of src/source.cc:951-1006.  threads > 1 splits the SAMPLE loop over worker threads
+    (every sample's sum keeps the reference's ascending-SNP order, so the result is bit-identical to the
+    single-threaded one); samples=(s0, s1) computes only that sample range (s0 % 4 == 0; the rest of the
+    returned arrays stays 0)."""
     rows = np.ascontiguousarray(rows, dtype=np.uint8)
     idx = None if row_index is None else np.ascontiguousarray(row_index, dtype=np.int64)
     mc = rows.shape[0] if idx is None else idx.size
@@ -212,8 +220,25 @@ def find_pheno(rows: np.ndarray, n: int, freq, x1, x2=None, row_index=None):
     x2 = None if x2 is None else np.ascontiguousarray(x2, dtype=np.float64)
     y1 = np.zeros(n, dtype=np.float64)
     y2 = None if x2 is None else np.zeros(n, dtype=np.float64)
-    lib().oracle_find_pheno(_ptr(rows), rows.shape[1], _ptr(idx), mc, n, _ptr(freq), _ptr(x1), _ptr(x2),
-                            _ptr(y1), _ptr(y2))
+    if threads <= 1 and samples is None:
+        lib().oracle_find_pheno(_ptr(rows), rows.shape[1], _ptr(idx), mc, n, _ptr(freq), _ptr(x1), _ptr(x2),
+                                _ptr(y1), _ptr(y2))
+        return y1, y2
+    s0, s1 = (0, n) if samples is None else samples
+    assert s0 % 4 == 0 and 0 <= s0 <= s1 <= n
+    L = lib()
+    threads = max(1, min(threads, (s1 - s0 + 255) // 256))
+    per = ((s1 - s0 + threads - 1) // threads + 3) // 4 * 4
+
+    def work(t):
+        a, b = s0 + t * per, min(s1, s0 + (t + 1) * per)
+        if a < b:
+            L.oracle_find_pheno_range(_ptr(rows), rows.shape[1], _ptr(idx), mc, a, b, _ptr(freq), _ptr(x1), _ptr(x2),
+                                      _ptr(y1), _ptr(y2))
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
     return y1, y2
 
 
@@ -287,3 +312,49 @@ def synth_rows(seed: int, first_row: int, n_rows: int, n: int, stride: int | Non
     [t.start() for t in ts]
     [t.join() for t in ts]
     return out
+
+
+def synth_cols(seed: int, s0: int, s1: int, first_row: int = 0, n_rows: int | None = None, row_ids=None,
+               threads: int = 0) -> np.ndarray:
+    """Sample columns [s0, s1) (s0 % 4 == 0) of synthetic rows, packed as a panel of s1 - s0 samples."""
+    assert s0 % 4 == 0 and s1 > s0
+    ids = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.int64)
+    n_rows = ids.size if ids is not None else n_rows
+    stride = row_bytes(s1 - s0)
+    out = np.zeros((n_rows, stride), dtype=np.uint8)
+    threads = threads or min(os.cpu_count() or 1, 16)
+    L = lib()
+    chunk = (n_rows + threads - 1) // threads
+
+    def work(t):
+        lo, hi = t * chunk, min(n_rows, (t + 1) * chunk)
+        if lo < hi:
+            L.oracle_synth_cols(seed, first_row + lo, None if ids is None else C.c_void_p(ids.ctypes.data + 8 * lo), hi - lo,
+                                s0, s1, C.c_void_p(out.ctypes.data + lo * stride), stride)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return out
+
+
+def find_freq_threaded(rows: np.ndarray, n: int, threads: int = 0):
+    """find_freq with the ROW loop split over worker threads (rows are independent: same bits)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    mc = rows.shape[0]
+    counts = np.zeros((mc, 4), dtype=np.int32)
+    freq = np.zeros(mc, dtype=np.float64)
+    threads = max(1, min(threads or min(os.cpu_count() or 1, 16), mc))
+    chunk = (mc + threads - 1) // threads
+    L = lib()
+
+    def work(t):
+        lo, hi = t * chunk, min(mc, (t + 1) * chunk)
+        if lo < hi:
+            L.oracle_find_freq(C.c_void_p(rows.ctypes.data + lo * rows.shape[1]), rows.shape[1], None, hi - lo, n,
+                               C.c_void_p(counts.ctypes.data + 16 * lo), C.c_void_p(freq.ctypes.data + 8 * lo))
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return counts, freq

@@ -145,6 +145,39 @@ void oracle_find_pheno(const unsigned char *rows, size_t row_stride,
     free(buffer);
 }
 
+/* The same loop restricted to samples [s0, s1), s0 a multiple of 4: every sample's sum is formed in
+ * the same ascending-SNP order with the same operations as source.cc:986-996, so the values are
+ * bit-identical to oracle_find_pheno's; only the sample loop is split (for worker threads and for
+ * column subsets of panels too large to process whole).  pheno1/pheno2 are indexed by absolute sample. */
+void oracle_find_pheno_range(const unsigned char *rows, size_t row_stride,
+                             const int64_t *row_index, size_t mc, size_t s0, size_t s1,
+                             const double *freq, const double *effect1, const double *effect2,
+                             double *pheno1, double *pheno2)
+{
+    const int bivariate = (effect2 != NULL && pheno2 != NULL); /* source.cc:959 */
+    const size_t ns = s1 > s0 ? s1 - s0 : 0;
+    unsigned char *buffer = (unsigned char *)malloc(ns ? ns : 1);
+    size_t j, s;
+    for (s = s0; s < s1; s++) {                  /* source.cc:962-966 */
+        pheno1[s] = 0;
+        if (bivariate) pheno2[s] = 0;
+    }
+    for (j = 0; j < mc; j++) {                   /* causal rows, ascending: :968-984 */
+        const unsigned char *row = rows + (size_t)(row_index ? row_index[j] : (int64_t)j) * row_stride;
+        double average_A1_dosage = 2 * freq[j];  /* source.cc:986 */
+        oracle_unpack_snps(row + s0 / 4, buffer, ns);
+        for (s = 0; s < ns; s++) {               /* source.cc:987-996 */
+            double num_of_A1_copies;
+            if (buffer[s] == 3) continue;        /* :991 */
+            num_of_A1_copies = (double)(2 - buffer[s]); /* :992 */
+            pheno1[s0 + s] += (num_of_A1_copies - average_A1_dosage) * effect1[j];        /* :994 */
+            if (bivariate)
+                pheno2[s0 + s] += (num_of_A1_copies - average_A1_dosage) * effect2[j];    /* :995 */
+        }
+    }
+    free(buffer);
+}
+
 /* ------------------------------------------------------ apply_heritability */
 
 double oracle_apply_heritability(float hsq, double *pheno, size_t n, const double *noise,
@@ -278,6 +311,31 @@ void oracle_synth_rows(uint64_t panel_seed, int64_t first_row, size_t n_rows,
             uint32_t u3 = (uint32_t)(h >> 40);
             unsigned a1 = (u1 < thr) + (u2 < thr);
             /* packed bits: 2 copies -> 00, 1 -> 10, 0 -> 11, missing -> 01 */
+            unsigned bits = (u3 < 16777u) ? 1u : (a1 == 2 ? 0u : (a1 == 1 ? 2u : 3u));
+            row[i >> 2] |= (unsigned char)(bits << (2 * (i & 3)));
+        }
+    }
+}
+
+/* Columns [s0, s1) (s0 % 4 == 0) of the same synthetic rows, packed as rows of a panel that holds only
+ * those samples: byte b of an output row equals byte s0/4 + b of the full row (its last byte masked to
+ * s1).  row_ids (optional) lists the SNP rows, otherwise first_row + r. */
+void oracle_synth_cols(uint64_t panel_seed, int64_t first_row, const int64_t *row_ids, size_t n_rows,
+                       size_t s0, size_t s1, unsigned char *rows, size_t row_stride)
+{
+    const size_t ns = s1 - s0, row_bytes = oracle_bed_row_bytes(ns);
+    long long r;
+    for (r = 0; r < (long long)n_rows; r++) {
+        unsigned char *row = rows + (size_t)r * row_stride;
+        uint64_t key = oracle_mix64(panel_seed ^ oracle_mix64((uint64_t)(row_ids ? row_ids[r] : first_row + r)));
+        uint32_t thr = 10486u + (uint32_t)(((key >> 32) * 513802ull) >> 32);
+        size_t i;
+        memset(row, 0, row_bytes);
+        for (i = 0; i < ns; i++) {
+            uint64_t h = oracle_mix64(key + (uint64_t)(s0 + i));
+            uint32_t u1 = (uint32_t)(h & 0xFFFFF), u2 = (uint32_t)((h >> 20) & 0xFFFFF);
+            uint32_t u3 = (uint32_t)(h >> 40);
+            unsigned a1 = (u1 < thr) + (u2 < thr);
             unsigned bits = (u3 < 16777u) ? 1u : (a1 == 2 ? 0u : (a1 == 1 ? 2u : 3u));
             row[i >> 2] |= (unsigned char)(bits << (2 * (i & 3)));
         }

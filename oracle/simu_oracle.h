@@ -70,6 +70,13 @@ void oracle_find_pheno(const unsigned char *rows, size_t row_stride,
                        const double *freq, const double *effect1, const double *effect2,
                        double *pheno1, double *pheno2);
 
+/* find_pheno restricted to samples [s0, s1), s0 % 4 == 0 (same per-sample operation order, hence the
+ * same bits; used to split the sample loop over worker threads and for column subsets). */
+void oracle_find_pheno_range(const unsigned char *rows, size_t row_stride,
+                             const int64_t *row_index, size_t mc, size_t s0, size_t s1,
+                             const double *freq, const double *effect1, const double *effect2,
+                             double *pheno1, double *pheno2);
+
 /* apply_heritability with the N noise draws supplied by the caller
  * (draws stay in the host RNG module).  src/source.cc:1008-1029.
  * Returns gen_coef; *env_out receives env_coef. */
@@ -100,6 +107,10 @@ long oracle_scale_effects(int op, const double *freq, double *effect1, double *e
  * CUDA generator in simu_b200/csrc/synth.cu produces identical bytes. ---- */
 void oracle_synth_rows(uint64_t panel_seed, int64_t first_row, size_t n_rows,
                        size_t num_samples, unsigned char *rows, size_t row_stride);
+
+/* Sample columns [s0, s1) (s0 % 4 == 0) of the same rows, as a panel of s1 - s0 samples. */
+void oracle_synth_cols(uint64_t panel_seed, int64_t first_row, const int64_t *row_ids, size_t n_rows,
+                       size_t s0, size_t s1, unsigned char *rows, size_t row_stride);
 
 #ifdef __cplusplus
 }

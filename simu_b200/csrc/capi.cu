@@ -409,8 +409,15 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
         close(fd);
         return ctx_fail(ctx, SIMU_B200_ERROR, "ERROR: Could not open %s (file shorter than a BED header)", bed_path);
     }
-    // bed_header.c:80-102: v1.00 magic 6c 1b, third byte 01 = one locus per row
-    if (!(hdr[0] == 0x6c && hdr[1] == 0x1b && hdr[2] == 0x01)) {
+    // bed_header.c:80-102 (get_version_and_order) and :56-71 (get_data_offset):
+    //   v1.00: magic 6c 1b, third byte = order (01: one locus per row), data at offset 3;
+    //   v0.99: first byte 00 or 01 = order, data at offset 1;
+    //   older: one sample per row, data at offset 0.
+    // simu runs only files with one locus per row (source.cc:196-200).
+    int64_t data_off = -1;
+    if (hdr[0] == 0x6c && hdr[1] == 0x1b) { if (hdr[2] == 0x01) data_off = 3; }
+    else if ((hdr[0] & ~0x01) == 0) { if (hdr[0] == 0x01) data_off = 1; }
+    if (data_off < 0) {
         close(fd);
         return ctx_fail(ctx, SIMU_B200_EFORMAT,
                         "ERROR: Unsupported format in %s, snps must be rows, samples must be columns", bed_path);
@@ -449,7 +456,7 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
             while (q + run < nr && (file_rows ? file_rows[done + q + run] : r0 + run) == r0 + run) run++;
             const int64_t total = run * B, cut = 4 << 20;
             for (int64_t o = 0; o < total; o += cut)
-                pieces.push_back({3 + r0 * B + o, std::min(cut, total - o), q * B + o});
+                pieces.push_back({data_off + r0 * B + o, std::min(cut, total - o), q * B + o});
             prev = r0 + run - 1;
             q += run;
         }

@@ -189,8 +189,10 @@ struct PlinkFile {
         const size_t got = fread(h, 1, 3, fp);
         fclose(fp);
         if (got != 3) throw std::runtime_error(fail);                      // bed.c:52-58
-        const bool v100 = h[0] == 0x6c && h[1] == 0x1b;                     // bed_header.c:80-102
-        const bool snp_major = v100 ? (h[2] == 0x01) : false;
+        // bed_header.c:80-102: v1.00 = magic 6c 1b + order byte; v0.99 = order byte first; older = sample-major
+        const bool v100 = h[0] == 0x6c && h[1] == 0x1b;
+        const bool v099 = !v100 && (h[0] & ~0x01) == 0;
+        const bool snp_major = v100 ? (h[2] == 0x01) : (v099 ? h[0] == 0x01 : false);
         if (!snp_major)                                                     // source.cc:196-200
             throw std::runtime_error("ERROR: Unsupported format in " + bfile +
                                      ", snps must be rows, samples must be columns");

@@ -210,3 +210,28 @@ def test_scale_effects_restatement():
     assert np.array_equal(o1, x1 * np.sqrt(het))
     f[7] = 0.0
     assert oracle.scale_effects(1, f, x1)[2] == 7 and oracle.scale_effects(2, f, x1)[2] == -1
+
+
+def test_find_pheno_thread_split():
+    """The oracle's sample loop split over threads / restricted to a column block keeps every sample's
+    ascending-SNP operation order: bit-identical to the single-threaded restatement of source.cc:986-996
+    (the full-size GPU parity tests rely on this)."""
+    n, m = 10_007, 257
+    rows = oracle.synth_rows(20240901, 3, m, n)
+    _, f = oracle.find_freq(rows, n)
+    rng = np.random.default_rng(0)
+    x1, x2 = rng.standard_normal(m), rng.standard_normal(m)
+    a1, a2 = oracle.find_pheno(rows, n, f, x1, x2)
+    for t in (2, 7, 16):
+        b1, b2 = oracle.find_pheno(rows, n, f, x1, x2, threads=t)
+        assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+    c1, _ = oracle.find_pheno(rows, n, f, x1, None, samples=(4000, 6001))
+    assert np.array_equal(c1[4000:6001], a1[4000:6001]) and not c1[:4000].any() and not c1[6001:].any()
+    # a column block generated on its own equals the same columns of the full rows, and gives the same sums
+    sub = oracle.synth_cols(20240901, 4000, 6048, first_row=3, n_rows=m)
+    assert np.array_equal(sub, rows[:, 1000:1512])
+    d1, d2 = oracle.find_pheno(sub, 2048, f, x1, x2, threads=3)
+    assert np.array_equal(d1, a1[4000:6048]) and np.array_equal(d2, a2[4000:6048])
+    ct, ft = oracle.find_freq_threaded(rows, n, 5)
+    c0, f0 = oracle.find_freq(rows, n)
+    assert np.array_equal(ct, c0) and np.array_equal(ft, f0)
