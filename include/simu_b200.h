@@ -55,10 +55,13 @@ enum simu_b200_mode {
     /* FP64, per-sample sum in ascending causal-SNP order, separate
      * subtract/multiply/add: bit-identical to source.cc:986-996 on one GPU. */
     SIMU_B200_MODE_EXACT = 0,
-    /* 4-SNP lookup tables in FP32 (entries rounded from FP64), FP32 partial
-     * sums flushed to FP64: |dy| <= 1e-5 * max|y| (tests state the bound).
-     * Table entries and 1024-term partial sums must fit FP32: use EXACT mode
-     * for effect sizes beyond ~1e33 in magnitude. */
+    /* Throughput mode, |dy| <= 1e-5 * max|y| (tests state the bound).
+     * SAMPLE16 panels: tcgen05 integer MMA -- per-SNP weights quantised to 40-bit fixed point
+     * (relative to the largest weight of the trait) and split into signed 8-bit digits, genotype
+     * planes as unsigned bytes, exact 32-bit integer accumulation in TMEM, FP64 only for the final
+     * recombination: the result is the exact sum of the quantised weights (error ~1e-12 of max|y|).
+     * ROWS / GROUP4 panels: 4-SNP lookup tables in FP32 (entries rounded from FP64), FP32 partial
+     * sums flushed to FP64 (~1e-7); entries and 1024-term partial sums must fit FP32. */
     SIMU_B200_MODE_FAST = 1
 };
 
@@ -73,7 +76,17 @@ enum simu_b200_layout {
      * staged, in causal order, which is what the reference reads (source.cc:852-863) -- so `rows`
      * must be NULL.  find_pheno's FAST kernel then needs no bit transposition (config 4: 8.3 ->
      * 6.7 ms); the interleave rides on the staging pass, which rewrites every row anyway. */
-    SIMU_B200_LAYOUT_GROUP4 = 1
+    SIMU_B200_LAYOUT_GROUP4 = 1,
+    /* Sixteen consecutive rows stored sample-major: 32-bit word i of group g holds the genotypes of
+     * sample i for rows 16g..16g+15 (row 16g in bits 0-1), RE-CODED on the way in as the A2-allele
+     * dosage: 0 = hom A1, 1 = het, 2 = hom A2, 3 = missing (.bed bits 00/10/11/01 -> 00/01/10/11), so
+     * that a genotype's contribution is affine in the code except for the one AND-detectable missing
+     * state.  Compact panels only (`rows` must be NULL), pitch = round_up(N, 128) words per group;
+     * samples >= N and unwritten rows hold 0.  This is the layout of the tensor-core phenotype kernel
+     * (MODE_FAST): a thread owns one sample = one TMEM lane and expands its 16-SNP words into the
+     * K-dimension of a tcgen05 integer MMA.  panel_put_rows / load_bed / get_rows convert to and from
+     * .bed rows, so nothing outside the library sees the coding. */
+    SIMU_B200_LAYOUT_SAMPLE16 = 2
 };
 
 typedef struct simu_b200_ctx simu_b200_ctx;
@@ -116,7 +129,8 @@ SIMU_B200_API void *simu_b200_panel_device_ptr(const simu_b200_ctx *ctx);
 SIMU_B200_API int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows);
 SIMU_B200_API int simu_b200_panel_alloc_layout(simu_b200_ctx *ctx, int64_t num_rows, int layout);
 SIMU_B200_API int simu_b200_panel_layout(const simu_b200_ctx *ctx);
-/* GROUP4: bytes between consecutive 4-row groups = round_up(N, 128). */
+/* GROUP4: bytes between consecutive 4-row groups = round_up(N, 128); SAMPLE16: bytes between consecutive
+ * 16-row groups = 4 * round_up(N, 128). */
 SIMU_B200_API int64_t simu_b200_group_stride(const simu_b200_ctx *ctx);
 SIMU_B200_API int simu_b200_panel_free(simu_b200_ctx *ctx);
 

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("SIMU_B200_LIB") or os.path.join(_PKG, "lib", "libsimu
 
 OK, END, ERROR, EINVAL, ECUDA, ENOMEM, EFORMAT = range(7)
 MODE_EXACT, MODE_FAST = 0, 1
-LAYOUT_ROWS, LAYOUT_GROUP4 = 0, 1
+LAYOUT_ROWS, LAYOUT_GROUP4, LAYOUT_SAMPLE16 = 0, 1, 2
 
 # every symbol include/simu_b200.h declares: (name, restype, argtypes)
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
@@ -172,7 +172,8 @@ class Context:
         return int(self.lib.simu_b200_panel_device_ptr(self.h) or 0)
 
     def panel_alloc(self, rows: int, layout: int = LAYOUT_ROWS):
-        """layout: LAYOUT_ROWS (row lists allowed) or LAYOUT_GROUP4 (compact causal panel, rows=None)."""
+        """layout: LAYOUT_ROWS (row lists allowed), or a compact causal panel (rows=None): LAYOUT_GROUP4
+        (lookup-table FAST kernel) or LAYOUT_SAMPLE16 (tensor-core FAST kernel)."""
         self._check(self.lib.simu_b200_panel_alloc_layout(self.h, rows, layout))
 
     @property

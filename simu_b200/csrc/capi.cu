@@ -91,7 +91,10 @@ const char *simu_b200_last_error(const simu_b200_ctx *ctx) { return ctx ? ctx->e
 
 int64_t simu_b200_row_bytes(int64_t num_samples) { return (num_samples + 3) / 4; }   // bed_header.c:219-223
 int64_t simu_b200_row_stride(const simu_b200_ctx *ctx) { return ctx ? ctx->row_stride : 0; }
-int64_t simu_b200_group_stride(const simu_b200_ctx *ctx) { return ctx ? ctx->group_stride : 0; }
+int64_t simu_b200_group_stride(const simu_b200_ctx *ctx)
+{
+    return !ctx ? 0 : ctx->layout == SIMU_B200_LAYOUT_SAMPLE16 ? ctx->s16_stride : ctx->group_stride;
+}
 int simu_b200_panel_layout(const simu_b200_ctx *ctx) { return ctx ? ctx->layout : SIMU_B200_LAYOUT_ROWS; }
 int64_t simu_b200_panel_rows(const simu_b200_ctx *ctx) { return ctx ? ctx->panel_rows : 0; }
 void *simu_b200_panel_device_ptr(const simu_b200_ctx *ctx) { return ctx ? ctx->panel : nullptr; }
@@ -101,8 +104,10 @@ int simu_b200_open(simu_b200_ctx **out, int device, int64_t num_samples)
 {
     if (!out) return ctx_fail(nullptr, SIMU_B200_EINVAL, "open: ctx pointer is NULL");
     *out = nullptr;
-    if (num_samples <= 0 || num_samples > 0x7FFFFFF0ll)
-        return ctx_fail(nullptr, SIMU_B200_EINVAL, "open: num_samples %lld out of range", (long long)num_samples);
+    // one packed row (at its 128-byte pitch) must fit a staging buffer: N <= 268,434,944
+    if (num_samples <= 0 || (num_samples + 3) / 4 + SIMU_ROW_ALIGN > (int64_t)SIMU_STAGE_BYTES)
+        return ctx_fail(nullptr, SIMU_B200_EINVAL, "open: num_samples %lld out of range (1 .. %lld)", (long long)num_samples,
+                        (long long)(4 * ((int64_t)SIMU_STAGE_BYTES - SIMU_ROW_ALIGN)));
     int n = 0;
     int rc = simu_b200_device_count(&n);
     if (rc != SIMU_B200_OK) return rc;
@@ -125,6 +130,7 @@ int simu_b200_open(simu_b200_ctx **out, int device, int64_t num_samples)
     ctx->row_bytes = simu_b200_row_bytes(num_samples);
     ctx->row_stride = (ctx->row_bytes + SIMU_ROW_ALIGN - 1) / SIMU_ROW_ALIGN * SIMU_ROW_ALIGN;
     ctx->group_stride = (num_samples + SIMU_ROW_ALIGN - 1) / SIMU_ROW_ALIGN * SIMU_ROW_ALIGN;
+    ctx->s16_stride = 4 * ctx->group_stride;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev_a)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_b)) != cudaSuccess ||
@@ -235,12 +241,13 @@ int simu_b200_panel_alloc_layout(simu_b200_ctx *ctx, int64_t num_rows, int layou
 {
     if (!ctx) return SIMU_B200_EINVAL;
     if (num_rows <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_alloc: num_rows must be positive");
-    if (layout != SIMU_B200_LAYOUT_ROWS && layout != SIMU_B200_LAYOUT_GROUP4)
+    if (layout != SIMU_B200_LAYOUT_ROWS && layout != SIMU_B200_LAYOUT_GROUP4 && layout != SIMU_B200_LAYOUT_SAMPLE16)
         return ctx_fail(ctx, SIMU_B200_EINVAL, "panel_alloc: unknown layout %d", layout);
     int rc = simu_b200_panel_free(ctx);
     if (rc) return rc;
-    const size_t bytes = layout == SIMU_B200_LAYOUT_GROUP4 ? (size_t)((num_rows + 3) / 4) * (size_t)ctx->group_stride
-                                                           : (size_t)num_rows * (size_t)ctx->row_stride;
+    const size_t bytes = layout == SIMU_B200_LAYOUT_SAMPLE16 ? (size_t)((num_rows + 15) / 16) * (size_t)ctx->s16_stride
+                         : layout == SIMU_B200_LAYOUT_GROUP4 ? (size_t)((num_rows + 3) / 4) * (size_t)ctx->group_stride
+                                                             : (size_t)num_rows * (size_t)ctx->row_stride;
     cudaError_t e = cudaMalloc((void **)&ctx->panel, bytes);
     if (e != cudaSuccess)
         return ctx_fail(ctx, SIMU_B200_ENOMEM, "panel_alloc: cannot allocate %zu bytes of HBM (%s)", bytes,
@@ -257,6 +264,16 @@ int simu_b200_panel_alloc_layout(simu_b200_ctx *ctx, int64_t num_rows, int layou
 int simu_b200_panel_alloc(simu_b200_ctx *ctx, int64_t num_rows)
 {
     return simu_b200_panel_alloc_layout(ctx, num_rows, SIMU_B200_LAYOUT_ROWS);
+}
+
+// Rows per staging chunk: as many as the 64 MB bounce buffers hold, a multiple of 16 when possible so that
+// GROUP4 / SAMPLE16 chunk boundaries fall on group boundaries (the interleave kernels read-modify-write
+// boundary groups, so any count is correct).  simu_b200_open rejects sample counts whose single row
+// exceeds a buffer.
+static int64_t stage_rows(int64_t pitch)
+{
+    const int64_t fit = std::max<int64_t>(1, (int64_t)SIMU_STAGE_BYTES / pitch);
+    return fit >= 16 ? (fit & ~(int64_t)15) : fit;
 }
 
 static int ensure_pinned(simu_b200_ctx *ctx)
@@ -342,8 +359,7 @@ int simu_b200_panel_put_rows(simu_b200_ctx *ctx, int64_t dst_row, int64_t n_rows
     cudaGetLastError();
     const uint8_t *src = (const uint8_t *)host_rows;
     if ((rc = ensure_dstage(ctx))) return rc;
-    // rows_per is a multiple of 4 so that GROUP4 chunk boundaries fall on group boundaries
-    const int64_t rows_per = std::max<int64_t>(4, ((int64_t)SIMU_STAGE_BYTES / ctx->row_bytes) & ~(int64_t)3);
+    const int64_t rows_per = stage_rows(ctx->row_bytes);
     int buf = 0;
     if (is_pinned) {
         // page-locked: chunked DMA straight from the caller's buffer into the device bounce
@@ -426,7 +442,7 @@ int simu_b200_panel_load_bed(simu_b200_ctx *ctx, const char *bed_path, int64_t n
     if ((rc = ensure_pinned(ctx)) || (rc = ensure_dstage(ctx)) || (rc = fork_copy_stream(ctx))) { close(fd); return rc; }
 
     const int64_t B = ctx->row_bytes;
-    const int64_t cap_rows = std::max<int64_t>(4, ((int64_t)SIMU_STAGE_BYTES / B) & ~(int64_t)3);
+    const int64_t cap_rows = stage_rows(B);
     int io_threads = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
     if (const char *e = getenv("SIMU_B200_IO_THREADS")) io_threads = std::max(1, atoi(e));
     int buf = 0;
@@ -513,7 +529,7 @@ static int synth_into_panel(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row
     if (rc) return rc;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
     const int64_t pitch = ctx->row_stride;
-    const int64_t rows_per = std::max<int64_t>(4, ((int64_t)SIMU_STAGE_BYTES / pitch) & ~(int64_t)3);
+    const int64_t rows_per = stage_rows(pitch);
     int64_t r = 0;
     while (r < n_rows) {
         const int64_t nr = std::min(rows_per, n_rows - r);
@@ -552,9 +568,10 @@ static int check_hot(simu_b200_ctx *ctx, const char *who, int64_t mc, const void
     if (!ctx) return SIMU_B200_EINVAL;
     if (!ctx->panel) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: no panel allocated", who);
     if (mc < 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: negative causal count", who);
-    if (rows && ctx->layout == SIMU_B200_LAYOUT_GROUP4)
-        return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: a GROUP4 panel is compact (stage the causal rows only, in causal "
-                        "order); row lists need a ROWS panel", who);
+    if (rows && ctx->layout != SIMU_B200_LAYOUT_ROWS)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "%s: a %s panel is compact (stage the causal rows only, in causal "
+                        "order); row lists need a ROWS panel", who,
+                        ctx->layout == SIMU_B200_LAYOUT_GROUP4 ? "GROUP4" : "SAMPLE16");
     cudaError_t e = cudaSetDevice(ctx->device);
     return ctx_cuda(ctx, e, "cudaSetDevice");
 }
@@ -581,6 +598,10 @@ int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t 
                         (long long)ctx->panel_rows);
     if (!d_freq || !d_effect1 || !d_pheno1 || ((d_effect2 == nullptr) != (d_pheno2 == nullptr)))
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: NULL argument (effect2/pheno2 must be both set or both NULL)");
+    if (ctx->layout == SIMU_B200_LAYOUT_SAMPLE16) {
+        if (mode == SIMU_B200_MODE_EXACT) return launch_pheno_exact_s16(ctx, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
+        if (mode == SIMU_B200_MODE_FAST) return launch_pheno_tc(ctx, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
+    }
     if (mode == SIMU_B200_MODE_EXACT)
         return launch_pheno_exact(ctx, d_rows, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
     if (mode == SIMU_B200_MODE_FAST)

@@ -195,7 +195,9 @@ int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t
     if (mc <= 0) return SIMU_B200_OK;
     const int ps = prof_begin(ctx, PROF_COUNTS);
     int rc = SIMU_B200_OK;
-    if (ctx->layout == SIMU_B200_LAYOUT_GROUP4) {
+    if (ctx->layout == SIMU_B200_LAYOUT_SAMPLE16) {
+        rc = launch_counts_s16(ctx, ctx->stream, mc, d_counts, d_freq);
+    } else if (ctx->layout == SIMU_B200_LAYOUT_GROUP4) {
         rc = launch_counts_g4_range(ctx, ctx->stream, 0, mc, d_counts, d_freq, 256);
     } else {
         const int warps_per_block = 8;

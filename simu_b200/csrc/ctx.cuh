@@ -26,6 +26,7 @@ struct simu_b200_ctx {
     int64_t panel_rows = 0;
     int layout = SIMU_B200_LAYOUT_ROWS;   // how the panel is laid out in HBM (simu_b200_layout)
     int64_t group_stride = 0; // GROUP4: bytes per 4-row group = round_up(N, 128), one byte per sample
+    int64_t s16_stride = 0;   // SAMPLE16: bytes per 16-row group = 4 * round_up(N, 128), one word per sample
 
     cudaStream_t own_stream = nullptr;   // created by open
     cudaStream_t stream = nullptr;       // stream in use (own or external)
@@ -51,6 +52,7 @@ struct simu_b200_ctx {
     bool prof_alloc = false;
 
     bool lut_attr_set[3] = {false, false, false};
+    bool tc_attr_set = false;
     bool fused_attr_set[3] = {false, false, false};
     int coop_sort_blocks = -1;           // co-resident blocks of the cooperative sort (-1: not queried)
     int64_t launches = 0;
@@ -63,7 +65,7 @@ struct simu_b200_ctx {
 
 enum ScratchSlot {
     SCR_ROWS = 0, SCR_COUNTS, SCR_FREQ, SCR_X1, SCR_X2, SCR_Y1, SCR_Y2, SCR_NOISE,
-    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG
+    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG, SCR_TCW
 };
 
 int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...);
@@ -89,6 +91,15 @@ int launch_counts(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, int32_t
 
 int launch_counts_g4_range(simu_b200_ctx *ctx, cudaStream_t stream, int64_t first_group, int64_t mc, int32_t *d_counts,
                            double *d_freq, int threads);
+
+// SAMPLE16 panels: bit-sliced vertical counting.  counts_s16.cu
+int launch_counts_s16(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int32_t *d_counts, double *d_freq);
+
+// kernel (b) on SAMPLE16 panels: tcgen05 integer MMA (FAST) and ordered FP64 (EXACT).  pheno_tc.cu, pheno_exact.cu
+int launch_pheno_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
+                    double *d_y1, double *d_y2);
+int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
+                           double *d_y1, double *d_y2);
 
 // kernel (b), exact FP64 ordered mode.  pheno_exact.cu
 int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,

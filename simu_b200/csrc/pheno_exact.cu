@@ -180,6 +180,70 @@ pheno_exact_g4_kernel(const uint8_t *__restrict__ panel, int64_t group_stride, i
     }
 }
 
+// SAMPLE16 layout: word i of group g holds sample i's dosage codes (0 hom A1, 1 het, 2 hom A2, 3 missing)
+// for rows 16g..16g+15, so a thread owns ONE sample, reads one coalesced 32-bit word per 16 SNPs and adds
+// the 16 contributions in ascending SNP order -- the same per-sample order and operations as above, hence
+// the same bits.  The table is indexed by the dosage code: entry 3 (missing) is +0.0.
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+pheno_exact_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int64_t mc, int64_t n_samples,
+                       const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
+                       double *__restrict__ y1, double *__restrict__ y2)
+{
+    __shared__ __align__(16) double tbl[kChunk][4][K];      // [snp][dosage code][trait]
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n_samples;
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(panel) + (active ? i : 0);
+    const int64_t gw = s16_stride >> 2;                        // words per group
+    double acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = 0.0;
+
+    uint32_t w[4], wn[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) w[q] = (16 * q < mc) ? __ldg(base + q * gw) : 0u;
+    for (int64_t j0 = 0; j0 < mc; j0 += kChunk) {
+        const int nj = (int)min((int64_t)kChunk, mc - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nj; t += blockDim.x) {
+            const int64_t j = j0 + t;
+            const double avg = __dmul_rn(2.0, freq[j]);          // source.cc:986
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const double x = (k == 0) ? x1[j] : x2[j];
+                tbl[t][0][k] = __dmul_rn(__dsub_rn(2.0, avg), x);   // code 0: two A1 copies
+                tbl[t][1][k] = __dmul_rn(__dsub_rn(1.0, avg), x);   // code 1: one copy
+                tbl[t][2][k] = __dmul_rn(__dsub_rn(0.0, avg), x);   // code 2: none
+                tbl[t][3][k] = 0.0;                                 // code 3: missing (:991)
+            }
+        }
+        // the next chunk's words travel while this chunk is added
+#pragma unroll
+        for (int q = 0; q < 4; q++) wn[q] = (j0 + kChunk + 16 * q < mc) ? __ldg(base + ((j0 + kChunk) / 16 + q) * gw) : 0u;
+        __syncthreads();
+        const char *tb = reinterpret_cast<const char *>(&tbl[0][0][0]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+#pragma unroll
+            for (int f = 0; f < 16; f++) {
+                const int jj = 16 * q + f;
+                if (jj < nj) {
+                    const uint32_t off = ((w[q] >> (2 * f)) & 3u) * (8u * K);
+                    const double *e = reinterpret_cast<const double *>(tb + jj * (32 * K) + off);
+#pragma unroll
+                    for (int k = 0; k < K; k++) acc[k] = __dadd_rn(acc[k], e[k]);   // source.cc:994-995
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = wn[q];
+    }
+    if (active) {
+        y1[i] = acc[0];
+        if (K == 2) y2[i] = acc[K - 1];
+    }
+}
+
 template <int K, int SPT>
 void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq, const double *d_x1,
                     const double *d_x2, double *d_y1, double *d_y2)
@@ -223,4 +287,20 @@ int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, co
     prof_end(ctx, ps);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_exact_kernel launch");
+}
+
+int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
+                           double *d_y1, double *d_y2)
+{
+    const int64_t blocks = (ctx->n_samples + kThreads - 1) / kThreads;
+    const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
+    if (d_x2 && d_y2)
+        pheno_exact_s16_kernel<2><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(ctx->panel, ctx->s16_stride, mc, ctx->n_samples,
+                                                                                  d_freq, d_x1, d_x2, d_y1, d_y2);
+    else
+        pheno_exact_s16_kernel<1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(ctx->panel, ctx->s16_stride, mc, ctx->n_samples,
+                                                                                  d_freq, d_x1, nullptr, d_y1, nullptr);
+    prof_end(ctx, ps);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "pheno_exact_s16_kernel launch");
 }

@@ -45,6 +45,7 @@
 
 #include "counts_g4.cuh"
 #include "ctx.cuh"
+#include "pipeline.cuh"
 
 namespace {
 
@@ -68,70 +69,6 @@ constexpr int kUnroll = LUT_UNROLL;                  // sub-steps unrolled in th
 constexpr int kRowsPerProducer = kBlockRows / kProducers;
 constexpr int kThreads = (kWarps + kProducers) * 32;
 constexpr int kSmemBytes = kStages * kStageBytes + 64 + kProducers * 32 * 8;
-
-// ------------------------------------------------------------- PTX helpers
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    if (mbar_test(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_test(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-
-// Producer-side wait: poll with back-off so that the waiting warp does not burn issue slots
-// the consumer warps need (the bare try_wait loop was 35 % of all executed instructions).
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
-{
-    if (mbar_test(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_test(bar, parity)) {
-        __nanosleep(100);
-        if (clock64() - t0 > 4000000000ll) __trap();
-    }
-}
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-                 : "memory");
-}
 
 // (a & m) | (b & ~m) in one LOP3
 __device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)
@@ -204,40 +141,6 @@ struct LutParams {
     int64_t steps;          // tiles * nblocks
 };
 
-// Every CTA walks its contiguous range of the (sample-tile major, row-block minor) step list in
-// ROTATED order: at local time it, it is at the step whose row block b satisfies b == it (mod len).
-// All CTAs (one per sample tile for any given block) therefore need the same ~nblocks/len table
-// blocks at the same time, so a table is fetched from HBM once and served to the other tiles' CTAs
-// from L2.  (tile, block) of the current step are carried along incrementally: 64-bit divisions
-// cost ~100 instructions each and used to be a quarter of all issued instructions.
-struct StepWalk {
-    struct Cursor { int64_t s, tile, blk; };
-    int64_t s_begin, s_end, len, nb, tile_b, blk_b;
-    Cursor first;
-    __device__ __forceinline__ StepWalk(const LutParams &p, int64_t cta, int64_t grid)
-    {
-        s_begin = (cta * p.steps) / grid; s_end = ((cta + 1) * p.steps) / grid;
-        len = s_end - s_begin;
-        nb = p.nblocks;
-        const int64_t rot = len > 0 ? (len - (s_begin - (s_begin / nb) * nb) % len) % len : 0;
-        tile_b = s_begin / nb; blk_b = s_begin - tile_b * nb;
-        first.s = s_begin + rot;
-        first.tile = tile_b + (blk_b + rot) / nb;
-        first.blk = (blk_b + rot) - (first.tile - tile_b) * nb;
-    }
-    __device__ __forceinline__ void advance(Cursor &c) const
-    {
-        c.s++; c.blk++;
-        if (c.blk == nb) { c.blk = 0; c.tile++; }
-        if (c.s == s_end) { c.s = s_begin; c.tile = tile_b; c.blk = blk_b; }
-    }
-};
-
-__device__ __forceinline__ int64_t cta_of_step(int64_t s, int64_t grid, int64_t steps)
-{
-    return ((s + 1) * grid - 1) / steps;   // largest c with (c*steps)/grid <= s
-}
-
 // Accumulators are float2 so that every add is one packed FADD2 (add.f32x2, sm_100):
 //   K=2: acc[s]       = (trait1, trait2) of sample s            (16 registers pairs)
 //   K=1: acc[2*q + h] = samples (q + 8h, q + 8h + 4), q = 0..3  ( 8 register pairs)
@@ -302,7 +205,7 @@ pheno_lut_kernel(const LutParams p)
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t grid = gridDim.x, cta = blockIdx.x;
-    StepWalk walk(p, cta, grid);
+    StepWalk walk(p.steps, p.nblocks, cta, grid);
     const int64_t len = walk.len;
     typedef StepWalk::Cursor Cursor;
     const Cursor first = walk.first;
@@ -504,7 +407,7 @@ pheno_lut_g4_kernel(const LutParams p)
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t grid = gridDim.x, cta = blockIdx.x;
-    StepWalk walk(p, cta, grid);
+    StepWalk walk(p.steps, p.nblocks, cta, grid);
     const int64_t len = walk.len;
     typedef StepWalk::Cursor Cursor;
 

@@ -1,0 +1,517 @@
+// Kernel (b), FAST mode on SAMPLE16 panels: find_pheno (src/source.cc:951-1006) as an exact INTEGER
+// matrix product on the 5th-generation tensor cores (tcgen05, accumulators in TMEM).
+//
+// Why tensor cores for a K <= 2 path.  The 4-SNP lookup-table kernel (pheno_lut.cu) moves 2 bytes through
+// the shared-memory data pipe per genotype and trait pair; ncu showed that pipe 94 % busy at 0.55 of the
+// HBM roofline for two traits (profiles/r01_g4_config2_ncu.txt): the path is NOT memory-bound on the CUDA
+// cores.  Here the genotypes never go back through shared memory after their one 4-byte load per 16 SNPs:
+// a thread expands its word in registers, stores the bytes to TENSOR MEMORY, and the MMA reads them there.
+//
+// The arithmetic.  With the panel's dosage code c in {0, 1, 2, 3 = missing} (stage.cu) and m = [c == 3],
+//     contribution_j = (a - 2 f_j) x_j [c != 3],  a = 2 - c      (source.cc:986-996)
+//                    = x_j (2 - 2 f_j)  +  (-x_j) c  +  x_j (1 + 2 f_j) m
+// so   y_i = C + sum_j Wp_j c_ij + sum_j Wm_j m_ij,   C = sum_j x_j (2 - 2 f_j), Wp = -x, Wm = x (1 + 2 f).
+// Wp, Wm are rounded to 40-bit fixed point relative to the largest |W| of the trait (quantum 2^e, a power
+// of two: error <= 2^-41 max|W| per weight, ~1e-12 of max|y| in total, against the stated 1e-5) and split
+// into six signed base-256 digits.  The MMA is tcgen05.mma.kind::i8, M = 128 samples, N = 16 columns
+// (trait x digit), K = 32 bytes = 16 SNPs x {c plane, m plane}:
+//     A (u8, from TMEM)   byte = c << 2s  resp.  m << 2s : the word ANDed with a byte mask, no shifts
+//     B (s8, from smem)   digit_d( W << (6 - 2s) ), canonical K-major no-swizzle core matrices
+//     D (s32, in TMEM)    64 * sum_j c_ij * digit_d(Wp_j) + ... : EXACT integer sums, order-independent
+// Every <= 256 steps (16384 SNPs: |D| < 2^29) the owners of the TMEM lanes read D back, recombine the
+// digits in 64-bit integers and add the result, scaled by 2^(e-6), to an FP64 register.
+//
+// One step of a CTA = 64 SNPs (4 groups) x 512 samples:
+//   producer warp   TMA bulk copies: 4 x 2 KB of genotype words + the 2 KB weight tile of the 64-SNP block
+//                   into a 12-stage shared-memory ring (mbarrier full / empty)
+//   16 expander     sub-tile t = warp / 4 owns samples 128 t .. 128 t + 127 = TMEM lanes 0..127; a thread
+//   warps           loads its 4 words (LDS.32, conflict-free), forms 8 masked words per raw word (9 LOP3/SHF
+//                   per 16 genotypes), writes them with ONE tcgen05.st.32x32b.x32 into one of two A buffers
+//   MMA warp        per sub-tile and step 4 x tcgen05.mma (8 clk each at N = 16), tcgen05.commit releases the
+//                   A buffer, the stage and, at flush points, D
+// Work is split over min(#SM, steps) persistent CTAs exactly as in pheno_lut.cu (contiguous ranges of the
+// (tile, block) step list, rotated start, per-(CTA, tile) FP64 slots added in a fixed order).
+//
+// Algorithmic bytes: Mc (ceil(N/4) + 12 + 8K) + 8NK.
+#include <math.h>
+#include <stdlib.h>
+
+#include "ctx.cuh"
+#include "pipeline.cuh"
+
+namespace {
+
+constexpr int kTile = 512;                          // samples per CTA tile
+constexpr int kSub = 4;                             // 128-sample sub-tiles (one TMEM lane set each)
+constexpr int kStepGroups = 4;                      // 16-SNP groups per step
+constexpr int kStepSnps = 16 * kStepGroups;         // 64
+constexpr int kExpWarps = 4 * kSub;                 // 16
+constexpr int kThreads = (kExpWarps + 2) * 32;      // + producer warp + MMA warp
+constexpr int kChunkBytes = kTile * 4;              // one group's words for the tile
+constexpr int kWTileBytes = kStepGroups * 512;      // weights of a 64-SNP block: 4 x [N = 16][K = 32] s8
+constexpr int kStageBytes = kStepGroups * kChunkBytes + kWTileBytes;   // 10 KB
+constexpr int kStages = 12;                         // 120 KB: also keeps a second CTA (and its TMEM request) off the SM
+constexpr int kFlushSteps = 256;
+constexpr int kDigits = 6;                          // signed base-256 digits per weight (of 8 columns per trait)
+constexpr int kFracBits = 40;                       // |W| / 2^e < 2^40
+constexpr int kTmemCols = 512;
+constexpr int kColD = 0;                            // D: kSub x 16 columns
+constexpr int kColA = 64;                           // A: kSub x 2 buffers x 32 columns
+// barriers (8 bytes each) after the ring
+constexpr int kBarFull = 0, kBarEmpty = kBarFull + kStages, kBarAFull = kBarEmpty + kStages,
+              kBarAEmpty = kBarAFull + 2 * kSub, kBarDFull = kBarAEmpty + 2 * kSub, kBarDEmpty = kBarDFull + 1,
+              kNumBars = kBarDEmpty + 1;
+constexpr int kSmemBytes = kStages * kStageBytes + kNumBars * 8 + 16;
+
+// ------------------------------------------------------------------ tcgen05 wrappers
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem], issued by one elected lane of a converged warp (operands warp-uniform)
+__device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                 "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                 "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor of one weight sub-tile: [N = 16][K = 32] s8, K-major, no swizzle, as 8 x 16-byte
+// core matrices: K chunks 256 B apart (leading-dimension byte offset), 8-column groups 128 B apart (stride)
+__device__ __forceinline__ uint64_t wtile_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(256u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = s32, A = u8, B = s8, both K-major, N = 16, M = 128
+constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------ weights
+
+struct TcScale {            // per trait, written by tc_prepare_kernel
+    double constant;        // C = sum_j x_j (2 - 2 f_j)
+    int exponent;           // e: weights are integers in units of 2^e
+    int pad;
+};
+
+__device__ __forceinline__ void weights_of(double f, double x, double &wp, double &wm, double &c)
+{
+    wp = -x;
+    wm = x * (1.0 + 2.0 * f);
+    c = x * (2.0 - 2.0 * f);
+}
+
+constexpr int kPrepBlocks = 128, kPrepThreads = 256;
+
+// pass 1: largest |W| per trait (-> the power-of-two quantum) and the constant term, summed in a fixed order
+template <int K>
+__global__ void __launch_bounds__(kPrepThreads)
+tc_prepare_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
+                  double *__restrict__ partial /* [K][kPrepBlocks] sums, then [K][kPrepBlocks] maxima */,
+                  unsigned int *__restrict__ ticket, TcScale *__restrict__ scale)
+{
+    __shared__ double ssum[K][kPrepThreads], smax[K][kPrepThreads];
+    __shared__ bool last;
+    double sum[K], mx[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { sum[k] = 0.0; mx[k] = 0.0; }
+    for (int64_t j = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; j < mc; j += (int64_t)kPrepBlocks * kPrepThreads) {
+        const double f = freq[j];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double wp, wm, c;
+            weights_of(f, k == 0 ? x1[j] : x2[j], wp, wm, c);
+            sum[k] += c;
+            mx[k] = fmax(mx[k], fmax(fabs(wp), fabs(wm)));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) { ssum[k][threadIdx.x] = sum[k]; smax[k][threadIdx.x] = mx[k]; }
+    __syncthreads();
+    for (int s = kPrepThreads / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                ssum[k][threadIdx.x] += ssum[k][threadIdx.x + s];
+                smax[k][threadIdx.x] = fmax(smax[k][threadIdx.x], smax[k][threadIdx.x + s]);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            partial[k * kPrepBlocks + blockIdx.x] = ssum[k][0];
+            partial[(K + k) * kPrepBlocks + blockIdx.x] = smax[k][0];
+        }
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == (unsigned)kPrepBlocks - 1u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < K) {
+        __threadfence();
+        const int k = threadIdx.x;
+        double s = 0.0, m = 0.0;
+        for (int b = 0; b < kPrepBlocks; b++) {
+            s += ((volatile double *)partial)[k * kPrepBlocks + b];
+            m = fmax(m, ((volatile double *)partial)[(K + k) * kPrepBlocks + b]);
+        }
+        scale[k].constant = s;
+        // |W| < 2^(ilogb(m) + 1)  ->  |W| / 2^e < 2^kFracBits
+        scale[k].exponent = (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 - kFracBits : 0;
+        scale[k].pad = 0;
+        if (k == 0) *ticket = 0;
+    }
+}
+
+// pass 2: the weight tiles.  One thread writes the 16 K-bytes of one (64-SNP block, group q, plane, column n).
+template <int K>
+__global__ void __launch_bounds__(128)
+tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
+                  const TcScale *__restrict__ scale, uint8_t *__restrict__ wt)
+{
+    const int64_t blk = blockIdx.x;
+    const int t = threadIdx.x;
+    const int q = t >> 5, plane = (t >> 4) & 1, n = t & 15;
+    const int k = n >> 3, d = n & 7;
+    uint32_t out[4] = {0, 0, 0, 0};
+    if (k < K && d < kDigits) {
+        const int e = scale[k].exponent;
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            const int s = kk >> 2, b = kk & 3;                         // byte b of the word masked for field s
+            const int64_t j = blk * kStepSnps + 16 * q + 4 * b + s;   // SNP 4b + s of the group
+            if (j < mc) {
+                double wp, wm, c;
+                weights_of(freq[j], k == 0 ? x1[j] : x2[j], wp, wm, c);
+                long long v = __double2ll_rn(ldexp(plane ? wm : wp, -e));   // |v| <= 2^40
+                v <<= 6 - 2 * s;                                        // the A byte carries the factor 4^s
+                long long digit = 0;
+#pragma unroll
+                for (int i = 0; i < kDigits; i++) {
+                    if (i <= d) {
+                        digit = (long long)(signed char)(v & 0xFF);
+                        v = (v - digit) >> 8;
+                    }
+                }
+                out[kk >> 2] |= (uint32_t)(uint8_t)digit << (8 * (kk & 3));
+            }
+        }
+    }
+    // sub-tile q at q*512; element (n, kappa): (kappa / 16) * 256 + (n / 8) * 128 + (n % 8) * 16 + kappa % 16
+    uint4 *dst = reinterpret_cast<uint4 *>(wt + blk * kWTileBytes + q * 512 + plane * 256 + (n >> 3) * 128 + (n & 7) * 16);
+    *dst = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+// ------------------------------------------------------------------ main kernel
+
+struct TcParams {
+    const uint8_t *panel;
+    int64_t s16_stride;
+    int64_t mc;
+    int64_t n_samples;
+    const uint8_t *wt;
+    const TcScale *scale;
+    double *ypart;          // [slots][K][npad]
+    int64_t npad;           // tiles * kTile
+    int64_t tiles;
+    int64_t nblocks;
+    int64_t steps;          // tiles * nblocks
+};
+
+// true when the accumulators must be drained BEFORE step `it`: the tile changed or kFlushSteps were added
+__device__ __forceinline__ bool flush_before(int64_t it, int64_t tile, int64_t cur_tile, int since_flush)
+{
+    return it > 0 && (tile != cur_tile || since_flush == kFlushSteps);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads, 1)
+pheno_tc_kernel(const TcParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
+    const int64_t grid = gridDim.x, cta = blockIdx.x;
+    StepWalk walk(p.steps, p.nblocks, cta, grid);
+    const int64_t len = walk.len;
+    typedef StepWalk::Cursor Cursor;
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base + kStages * kStageBytes;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kStages * kStageBytes + kNumBars * 8);
+    auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(bar(kBarFull + s), 1); mbar_init(bar(kBarEmpty + s), kExpWarps + 1); }
+        for (int i = 0; i < 2 * kSub; i++) { mbar_init(bar(kBarAFull + i), 4); mbar_init(bar(kBarAEmpty + i), 1); }
+        mbar_init(bar(kBarDFull), 1);
+        mbar_init(bar(kBarDEmpty), kExpWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kExpWarps + 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int64_t ngroups_total = (p.mc + 15) >> 4;
+
+    if (warp == kExpWarps) {
+        // ============ producer warp: lane q copies group q's 2 KB of words, lane 4 the weight tile ============
+        uint64_t pol_stream, pol_keep;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        Cursor c = walk.first;
+        for (int64_t it = 0; it < len; it++, walk.advance(c)) {
+            const int stage = (int)(it % kStages);
+            const uint32_t parity = (uint32_t)((it / kStages) & 1);
+            const uint32_t stage_base = smem_base + stage * kStageBytes;
+            const uint32_t bytes = (uint32_t)min((int64_t)kChunkBytes, p.s16_stride - c.tile * kChunkBytes);
+            const int ng = (int)min((int64_t)kStepGroups, ngroups_total - c.blk * kStepGroups);
+            if (lane == 0) {
+                mbar_wait_backoff(bar(kBarEmpty + stage), parity ^ 1u);
+                mbar_arrive_expect_tx(bar(kBarFull + stage), (uint32_t)ng * bytes + (uint32_t)kWTileBytes);
+            }
+            __syncwarp();
+            if (lane < ng)
+                bulk_g2s(stage_base + lane * kChunkBytes, p.panel + (c.blk * kStepGroups + lane) * p.s16_stride + c.tile * kChunkBytes,
+                         bytes, bar(kBarFull + stage), pol_stream);
+            else if (lane == kStepGroups)
+                bulk_g2s(stage_base + kStepGroups * kChunkBytes, p.wt + c.blk * kWTileBytes, kWTileBytes, bar(kBarFull + stage), pol_keep);
+        }
+    } else if (warp == kExpWarps + 1) {
+        // ============ MMA warp: all lanes run the loop, one elected lane issues ============
+        Cursor c = walk.first;
+        int64_t cur_tile = -1;
+        int since_flush = 0;
+        uint32_t dphase = 0;
+        for (int64_t it = 0; it < len; it++, walk.advance(c)) {
+            const int stage = (int)(it % kStages);
+            const uint32_t parity = (uint32_t)((it / kStages) & 1);
+            const uint32_t abuf = (uint32_t)(it & 1), aparity = (uint32_t)((it >> 1) & 1);
+            bool fresh = it == 0;                               // first MMA of each sub-tile overwrites D
+            if (flush_before(it, c.tile, cur_tile, since_flush)) {
+                mbar_wait(bar(kBarDEmpty), dphase);             // D has been read back
+                dphase ^= 1u;
+                since_flush = 0;
+                fresh = true;
+            }
+            cur_tile = c.tile;
+            since_flush++;
+            mbar_wait(bar(kBarFull + stage), parity);           // weight tile landed
+            const uint32_t wbase = smem_base + stage * kStageBytes + kStepGroups * kChunkBytes;
+#pragma unroll
+            for (int t = 0; t < kSub; t++) {
+                mbar_wait(bar(kBarAFull + 2 * t + abuf), aparity);
+                tc_fence_after();
+                const uint32_t a = tmem + kColA + (2 * t + abuf) * 32, d = tmem + kColD + 16 * t;
+#pragma unroll
+                for (int q = 0; q < kStepGroups; q++)
+                    mma_i8_ts(d, a + 8 * q, wtile_desc(wbase + q * 512), kIdesc, (fresh && q == 0) ? 0u : 1u);
+                mma_commit(bar(kBarAEmpty + 2 * t + abuf));     // A buffer free once these MMAs have read it
+            }
+            mma_commit(bar(kBarEmpty + stage));                 // weight tile free
+            // the accumulators are complete when the next step starts with a flush, or the range ends
+            Cursor nx = c;
+            walk.advance(nx);
+            if (it + 1 == len || nx.tile != c.tile || since_flush == kFlushSteps) mma_commit(bar(kBarDFull));
+        }
+    } else {
+        // ============ expander warps ============
+        const int t = warp >> 2;                                // sub-tile
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;         // this warp's quarter of the TMEM lanes
+        const int my = t * 128 + (warp & 3) * 32 + lane;        // sample within the tile
+        double y[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) y[k] = 0.0;
+        int escale[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) escale[k] = p.scale[k].exponent - 6;
+        uint32_t dphase = 0;
+        int64_t cur_tile = -1, slot = 0;
+        int since_flush = 0;
+
+        // read D back, recombine the digits exactly, add to y
+        auto drain = [&]() {
+            mbar_wait(bar(kBarDFull), dphase);
+            dphase ^= 1u;
+            tc_fence_after();
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_field + kColD + 16 * t, r);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarDEmpty));
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const long long lo = (long long)(int)r[8 * k] + ((long long)(int)r[8 * k + 1] << 8) + ((long long)(int)r[8 * k + 2] << 16);
+                const long long hi = (long long)(int)r[8 * k + 3] + ((long long)(int)r[8 * k + 4] << 8) + ((long long)(int)r[8 * k + 5] << 16);
+                y[k] += ldexp((double)hi * 16777216.0 + (double)lo, escale[k]);
+            }
+        };
+        auto store = [&]() {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                // +=: the rotated walk may visit the tile of its starting point twice (the slots start at 0)
+                p.ypart[(slot * K + k) * p.npad + cur_tile * kTile + my] += y[k];
+                y[k] = 0.0;
+            }
+        };
+
+        Cursor c = walk.first;
+        for (int64_t it = 0; it < len; it++, walk.advance(c)) {
+            const int stage = (int)(it % kStages);
+            const uint32_t parity = (uint32_t)((it / kStages) & 1);
+            const uint32_t abuf = (uint32_t)(it & 1), aparity = (uint32_t)((it >> 1) & 1);
+            if (flush_before(it, c.tile, cur_tile, since_flush)) {
+                drain();
+                if (c.tile != cur_tile) store();
+                since_flush = 0;
+            }
+            if (c.tile != cur_tile) {
+                cur_tile = c.tile;
+                slot = cta - cta_of_step(c.tile * p.nblocks, grid, p.steps);
+            }
+            since_flush++;
+
+            mbar_wait(bar(kBarFull + stage), parity);
+            const uint32_t src = smem_base + stage * kStageBytes + my * 4;
+            uint32_t w[kStepGroups];
+#pragma unroll
+            for (int q = 0; q < kStepGroups; q++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(src + q * kChunkBytes));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarEmpty + stage));                // the words are in registers
+            uint32_t r[32];
+#pragma unroll
+            for (int q = 0; q < kStepGroups; q++) {
+                const uint32_t x = w[q], h = x >> 1;
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    r[8 * q + s] = x & (0x03030303u << (2 * s));               // c << 2s
+                    r[8 * q + 4 + s] = x & h & (0x01010101u << (2 * s));       // [c == 3] << 2s
+                }
+            }
+            mbar_wait(bar(kBarAEmpty + 2 * t + abuf), aparity ^ 1u);           // the MMAs of step it-2 have read this buffer
+            tc_fence_after();
+            tmem_st32(tmem + lane_field + kColA + (2 * t + abuf) * 32, r);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarAFull + 2 * t + abuf));
+        }
+        drain();
+        store();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kExpWarps + 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// y[k][i] = C_k + sum over the slots of the tile that holds sample i, in slot order
+template <int K>
+__global__ void __launch_bounds__(256)
+tc_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int slots, const TcScale *__restrict__ scale,
+                 double *__restrict__ y1, double *__restrict__ y2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double s = 0.0;
+        for (int q = 0; q < slots; q++) s += ypart[((int64_t)q * K + k) * npad + i];
+        s += scale[k].constant;
+        if (k == 0) y1[i] = s; else y2[i] = s;
+    }
+}
+
+template <int K>
+int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2, double *d_y1,
+           double *d_y2)
+{
+    const int64_t n = ctx->n_samples;
+    const int64_t tiles = (n + kTile - 1) / kTile;
+    const int64_t nblocks = (mc + kStepSnps - 1) / kStepSnps;
+    const int64_t steps = tiles * nblocks;
+    const int64_t grid = steps < ctx->num_sms ? steps : ctx->num_sms;
+    const int slots = (int)((grid + tiles - 1) / tiles) + 1;
+    const int64_t npad = tiles * kTile;
+
+    // weight tiles, then: [TcScale x 2][ticket + pad][partials 4 x kPrepBlocks doubles]
+    const size_t wt_bytes = (size_t)nblocks * kWTileBytes;
+    const size_t aux_off = (wt_bytes + 255) & ~(size_t)255;
+    uint8_t *wt = (uint8_t *)ctx_scratch(ctx, SCR_TCW, aux_off + 64 + 4 * kPrepBlocks * sizeof(double));
+    const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
+    double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
+    if (!wt || !ypart) return SIMU_B200_ENOMEM;
+    TcScale *scale = reinterpret_cast<TcScale *>(wt + aux_off);
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(wt + aux_off + 32);
+    double *partial = reinterpret_cast<double *>(wt + aux_off + 64);
+    if (!ctx->tc_attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        ctx->tc_attr_set = true;
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
+    int ps = prof_begin(ctx, PROF_LUT_BUILD);
+    tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);
+    tc_weights_kernel<K><<<(unsigned)nblocks, 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, scale, wt);
+    prof_end(ctx, ps);
+
+    TcParams p;
+    p.panel = ctx->panel; p.s16_stride = ctx->s16_stride; p.mc = mc; p.n_samples = n; p.wt = wt; p.scale = scale;
+    p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
+    ps = prof_begin(ctx, PROF_LUT_MAIN);
+    pheno_tc_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p);
+    prof_end(ctx, ps);
+    ps = prof_begin(ctx, PROF_LUT_REDUCE);
+    tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2);
+    prof_end(ctx, ps);
+    ctx->launches += 4;
+    return ctx_cuda(ctx, cudaGetLastError(), "pheno_tc launch");
+}
+
+}  // namespace
+
+int launch_pheno_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
+                    double *d_y1, double *d_y2)
+{
+    if (mc <= 0) {   // source.cc:962-966: phenotypes start at zero
+        CUDA_TRY(ctx, cudaMemsetAsync(d_y1, 0, (size_t)ctx->n_samples * sizeof(double), ctx->stream));
+        if (d_y2) CUDA_TRY(ctx, cudaMemsetAsync(d_y2, 0, (size_t)ctx->n_samples * sizeof(double), ctx->stream));
+        return SIMU_B200_OK;
+    }
+    if (d_x2 && d_y2) return run_tc<2>(ctx, mc, d_freq, d_x1, d_x2, d_y1, d_y2);
+    return run_tc<1>(ctx, mc, d_freq, d_x1, nullptr, d_y1, nullptr);
+}
