@@ -263,11 +263,12 @@ def run_ours(args, w):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     causal = _causal_rows(w, rank)
-    g4 = args.layout == "group4"
+    g4 = args.layout in ("group4", "s16")           # compact causal panel
+    compact_layout = capi.LAYOUT_SAMPLE16 if args.layout == "s16" else capi.LAYOUT_GROUP4
     if g4:
         # what the drop-in CLI keeps in HBM: the causal rows only (the reference reads no others,
         # source.cc:852-863), compact and in causal order, four rows sample-interleaved per group
-        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        ctx.panel_alloc(mc, compact_layout)
         if mc == m:
             ctx.panel_synth(PANEL_SEED, rank * m, m)
         else:
@@ -407,7 +408,7 @@ def run_ours(args, w):
         torch.cuda.synchronize()
         del panel_view
     ctx2 = capi.Context(n, device=local)
-    ctx2.panel_alloc(mc, capi.LAYOUT_GROUP4 if g4 else capi.LAYOUT_ROWS)
+    ctx2.panel_alloc(mc, compact_layout if g4 else capi.LAYOUT_ROWS)
     noise_h = d_noise.cpu().numpy()
     e2e_y = None
 
@@ -543,7 +544,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--layout", default="group4", choices=["group4", "rows"],
+    ap.add_argument("--layout", default="group4", choices=["group4", "rows", "s16"],
                     help="HBM panel: compact causal rows in GROUP4 layout (what the CLI stages) or the whole "
                          ".bed slice row-major with a causal row list")
     ap.add_argument("--fused", action="store_true",

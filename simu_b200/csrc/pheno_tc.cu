@@ -24,15 +24,19 @@
 // One step of a CTA = 64 SNPs (4 groups) x 512 samples:
 //   producer warp   TMA bulk copies: 4 x 2 KB of genotype words + the 2 KB weight tile of the 64-SNP block
 //                   into a 12-stage shared-memory ring (mbarrier full / empty)
-//   16 expander     sub-tile t = warp / 4 owns samples 128 t .. 128 t + 127 = TMEM lanes 0..127; a thread
-//   warps           loads its 4 words (LDS.32, conflict-free), forms 8 masked words per raw word (9 LOP3/SHF
-//                   per 16 genotypes), writes them with ONE tcgen05.st.32x32b.x32 into one of two A buffers
-//   MMA warp        per sub-tile and step 4 x tcgen05.mma (8 clk each at N = 16), tcgen05.commit releases the
-//                   A buffer, the stage and, at flush points, D
+//   16 expander     sub-tile t = warp / 4 owns samples 128 t .. 128 t + 127 = TMEM lanes 0..127 and is an
+//   warps           independent pipeline: a thread loads its 4 words (LDS.32, conflict-free, one step ahead),
+//                   forms 8 masked words per raw word (9 LOP3/SHF per 16 genotypes), writes them with ONE
+//                   tcgen05.st.32x32b.x32 into one of two A buffers; after a 128-thread named barrier the
+//                   sub-tile's first warp issues 4 x tcgen05.mma (8 clk each at N = 16) from one elected lane,
+//                   and tcgen05.commit releases the A buffer, the stage's weight tile and, at drain points, D
+//                   (a single MMA-issuing warp for all sub-tiles was 2.4x slower: five dependent mbarrier
+//                   waits of ~90 clk per step on one warp)
 // Work is split over min(#SM, steps) persistent CTAs exactly as in pheno_lut.cu (contiguous ranges of the
 // (tile, block) step list, rotated start, per-(CTA, tile) FP64 slots added in a fixed order).
 //
 // Algorithmic bytes: Mc (ceil(N/4) + 12 + 8K) + 8NK.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -43,24 +47,28 @@ namespace {
 
 constexpr int kTile = 512;                          // samples per CTA tile
 constexpr int kSub = 4;                             // 128-sample sub-tiles (one TMEM lane set each)
-constexpr int kStepGroups = 4;                      // 16-SNP groups per step
+constexpr int kStepGroups = 4;                      // 16-SNP groups per MMA step (one A buffer)
 constexpr int kStepSnps = 16 * kStepGroups;         // 64
+constexpr int kHalves = 2;                          // MMA steps per shared-memory stage
+constexpr int kStageGroups = kHalves * kStepGroups; // 8 groups = 128 SNPs per stage: ONE tensor copy
+constexpr int kStageSnps = 16 * kStageGroups;       // 128
 constexpr int kExpWarps = 4 * kSub;                 // 16
-constexpr int kThreads = (kExpWarps + 2) * 32;      // + producer warp + MMA warp
+constexpr int kMmaWarp0 = kExpWarps;                // one MMA-issuing warp per sub-tile
+constexpr int kProducerWarp = kExpWarps + kSub;
+constexpr int kThreads = (kExpWarps + kSub + 1) * 32;
 constexpr int kChunkBytes = kTile * 4;              // one group's words for the tile
-constexpr int kWTileBytes = kStepGroups * 512;      // weights of a 64-SNP block: 4 x [N = 16][K = 32] s8
-constexpr int kStageBytes = kStepGroups * kChunkBytes + kWTileBytes;   // 10 KB
-constexpr int kStages = 12;                         // 120 KB: also keeps a second CTA (and its TMEM request) off the SM
-constexpr int kFlushSteps = 256;
+constexpr int kWTileBytes = kStepGroups * 512;      // weights of 64 SNPs: 4 x [N = 16][K = 32] s8
+constexpr int kStageBytes = kStageGroups * kChunkBytes + kHalves * kWTileBytes;   // 16 KB + 4 KB
+constexpr int kStages = 6;                          // 120 KB: also keeps a second CTA (and its TMEM request) off the SM
+constexpr int kFlushSteps = 128;                    // stages between drains: 16384 SNPs, |D| < 2^29
 constexpr int kDigits = 6;                          // signed base-256 digits per weight (of 8 columns per trait)
 constexpr int kFracBits = 40;                       // |W| / 2^e < 2^40
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0;                            // D: kSub x 16 columns
 constexpr int kColA = 64;                           // A: kSub x 2 buffers x 32 columns
 // barriers (8 bytes each) after the ring
-constexpr int kBarFull = 0, kBarEmpty = kBarFull + kStages, kBarAFull = kBarEmpty + kStages,
-              kBarAEmpty = kBarAFull + 2 * kSub, kBarDFull = kBarAEmpty + 2 * kSub, kBarDEmpty = kBarDFull + 1,
-              kNumBars = kBarDEmpty + 1;
+constexpr int kBarFull = 0, kBarEmpty = kBarFull + kStages, kBarAEmpty = kBarEmpty + kStages,
+              kBarDFull = kBarAEmpty + 2 * kSub, kNumBars = kBarDFull + kSub;
 constexpr int kSmemBytes = kStages * kStageBytes + kNumBars * 8 + 16;
 
 // ------------------------------------------------------------------ tcgen05 wrappers
@@ -110,11 +118,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Wait with a counted bound (a protocol bug must trap, not hang the GPU): try_wait itself suspends the warp for
+// a hardware-defined time, so 2^22 failed polls are far beyond any legitimate wait.  (Letting one lane poll and
+// the warp reconverge behind it was measured 50 % SLOWER than all lanes polling.)
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity)
+{
+    for (int i = 0; i < (1 << 22); i++)
+        if (mbar_test(bar, parity)) return;
+    __trap();
+}
+
 // shared-memory matrix descriptor of one weight sub-tile: [N = 16][K = 32] s8, K-major, no swizzle, as 8 x 16-byte
 // core matrices: K chunks 256 B apart (leading-dimension byte offset), 8-column groups 128 B apart (stride)
 __device__ __forceinline__ uint64_t wtile_desc(uint32_t saddr)
 {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(256u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+// one box of the panel's tensor map (256 x 8-byte elements = 512 samples, kStageGroups rows) -> shared memory
+__device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar), "l"(policy) : "memory");
 }
 // instruction descriptor: D = s32, A = u8, B = s8, both K-major, N = 16, M = 128
 constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
@@ -248,111 +272,131 @@ struct TcParams {
     double *ypart;          // [slots][K][npad]
     int64_t npad;           // tiles * kTile
     int64_t tiles;
-    int64_t nblocks;
+    int64_t nblocks;        // 128-SNP stage blocks
     int64_t steps;          // tiles * nblocks
 };
 
-// true when the accumulators must be drained BEFORE step `it`: the tile changed or kFlushSteps were added
-__device__ __forceinline__ bool flush_before(int64_t it, int64_t tile, int64_t cur_tile, int since_flush)
-{
-    return it > 0 && (tile != cur_tile || since_flush == kFlushSteps);
-}
+// The CTA's contiguous range of the (sample-tile major, SNP-block minor) step list, walked in the rotated
+// order of StepWalk (pipeline.cuh) with 32-bit state: every warp of the CTA steps through it on its own, and a
+// single warp executes ~1 dependent instruction per 5 clocks, so the 64-bit divisions of a naive cursor
+// (it % stages, it / stages, ...) made the producer warp the bottleneck (measured: 1039 clk per step).
+struct Walk32 {
+    int len, nb, tile_b, blk_b;     // range length, blocks per tile, (tile, block) of the range start
+    int tile, blk, left;            // cursor; steps left before the walk wraps to the range start
+    __device__ __forceinline__ Walk32(int64_t steps, int64_t nblocks, int64_t cta, int64_t grid)
+    {
+        const int64_t s_begin = (cta * steps) / grid, s_end = ((cta + 1) * steps) / grid;
+        len = (int)(s_end - s_begin);
+        nb = (int)nblocks;
+        tile_b = (int)(s_begin / nblocks);
+        blk_b = (int)(s_begin - (int64_t)tile_b * nblocks);
+        const int rot = len > 0 ? (len - blk_b % len) % len : 0;
+        tile = tile_b + (blk_b + rot) / nb;
+        blk = (blk_b + rot) - (tile - tile_b) * nb;
+        left = len - rot;
+    }
+    __device__ __forceinline__ void advance()
+    {
+        if (++blk == nb) { blk = 0; tile++; }
+        if (--left == 0) { tile = tile_b; blk = blk_b; }
+    }
+};
+
+struct Ring {                       // position in the shared-memory ring
+    int stage = 0;
+    uint32_t parity = 0;
+    __device__ __forceinline__ void next() { if (++stage == kStages) { stage = 0; parity ^= 1u; } }
+};
 
 template <int K>
 __global__ void __launch_bounds__(kThreads, 1)
-pheno_tc_kernel(const TcParams p)
+pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
     const int64_t grid = gridDim.x, cta = blockIdx.x;
-    StepWalk walk(p.steps, p.nblocks, cta, grid);
-    const int64_t len = walk.len;
-    typedef StepWalk::Cursor Cursor;
+    Walk32 walk(p.steps, p.nblocks, cta, grid);
+    const int len = walk.len;
 
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bars = smem_base + kStages * kStageBytes;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kStages * kStageBytes + kNumBars * 8);
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(bar(kBarFull + s), 1); mbar_init(bar(kBarEmpty + s), kExpWarps + 1); }
-        for (int i = 0; i < 2 * kSub; i++) { mbar_init(bar(kBarAFull + i), 4); mbar_init(bar(kBarAEmpty + i), 1); }
-        mbar_init(bar(kBarDFull), 1);
-        mbar_init(bar(kBarDEmpty), kExpWarps);
+        for (int s = 0; s < kStages; s++) { mbar_init(bar(kBarFull + s), 1); mbar_init(bar(kBarEmpty + s), kExpWarps + kSub); }
+        for (int i = 0; i < 2 * kSub; i++) mbar_init(bar(kBarAEmpty + i), 1);
+        for (int i = 0; i < kSub; i++) mbar_init(bar(kBarDFull + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == kExpWarps + 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == kProducerWarp) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int64_t ngroups_total = (p.mc + 15) >> 4;
 
-    if (warp == kExpWarps) {
-        // ============ producer warp: lane q copies group q's 2 KB of words, lane 4 the weight tile ============
+    if (warp == kProducerWarp) {
+        // ============ producer warp: per stage ONE tensor copy (8 groups x 2 KB of words; rows and columns
+        // beyond the panel arrive as zeros) and one 4 KB bulk copy of the stage's weight tiles.  A bulk copy
+        // costs its issuing warp ~200 clk whatever its size (measured: five 2 KB copies per 64 SNPs made
+        // this warp the bottleneck at 1024 clk per step), so the copies are few and large.
         uint64_t pol_stream, pol_keep;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-        Cursor c = walk.first;
-        for (int64_t it = 0; it < len; it++, walk.advance(c)) {
-            const int stage = (int)(it % kStages);
-            const uint32_t parity = (uint32_t)((it / kStages) & 1);
-            const uint32_t stage_base = smem_base + stage * kStageBytes;
-            const uint32_t bytes = (uint32_t)min((int64_t)kChunkBytes, p.s16_stride - c.tile * kChunkBytes);
-            const int ng = (int)min((int64_t)kStepGroups, ngroups_total - c.blk * kStepGroups);
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&panel_map) : "memory");
+        Ring ring;
+        for (int it = 0; it < len; it++, walk.advance(), ring.next()) {
+            const uint32_t stage_base = smem_base + ring.stage * kStageBytes;
             if (lane == 0) {
-                mbar_wait_backoff(bar(kBarEmpty + stage), parity ^ 1u);
-                mbar_arrive_expect_tx(bar(kBarFull + stage), (uint32_t)ng * bytes + (uint32_t)kWTileBytes);
+                mbar_wait_backoff(bar(kBarEmpty + ring.stage), ring.parity ^ 1u);
+                mbar_arrive_expect_tx(bar(kBarFull + ring.stage), (uint32_t)kStageBytes);
+                tensor_g2s(stage_base, &panel_map, walk.tile * (kTile / 2), walk.blk * kStageGroups, bar(kBarFull + ring.stage), pol_stream);
+                bulk_g2s(stage_base + kStageGroups * kChunkBytes, p.wt + (int64_t)walk.blk * (kHalves * kWTileBytes), kHalves * kWTileBytes,
+                         bar(kBarFull + ring.stage), pol_keep);
             }
             __syncwarp();
-            if (lane < ng)
-                bulk_g2s(stage_base + lane * kChunkBytes, p.panel + (c.blk * kStepGroups + lane) * p.s16_stride + c.tile * kChunkBytes,
-                         bytes, bar(kBarFull + stage), pol_stream);
-            else if (lane == kStepGroups)
-                bulk_g2s(stage_base + kStepGroups * kChunkBytes, p.wt + c.blk * kWTileBytes, kWTileBytes, bar(kBarFull + stage), pol_keep);
         }
-    } else if (warp == kExpWarps + 1) {
-        // ============ MMA warp: all lanes run the loop, one elected lane issues ============
-        Cursor c = walk.first;
-        int64_t cur_tile = -1;
-        int since_flush = 0;
-        uint32_t dphase = 0;
-        for (int64_t it = 0; it < len; it++, walk.advance(c)) {
-            const int stage = (int)(it % kStages);
-            const uint32_t parity = (uint32_t)((it / kStages) & 1);
-            const uint32_t abuf = (uint32_t)(it & 1), aparity = (uint32_t)((it >> 1) & 1);
-            bool fresh = it == 0;                               // first MMA of each sub-tile overwrites D
-            if (flush_before(it, c.tile, cur_tile, since_flush)) {
-                mbar_wait(bar(kBarDEmpty), dphase);             // D has been read back
-                dphase ^= 1u;
-                since_flush = 0;
-                fresh = true;
-            }
-            cur_tile = c.tile;
+    } else if (warp >= kMmaWarp0) {
+        // ============ MMA warps: warp kMmaWarp0 + t serves sub-tile t.  The whole warp runs the loop (uniform
+        // operands -> uniform registers), one elected lane issues.  The hand-over from the expanders is a named
+        // barrier of 160 threads on which the 128 expander threads only ARRIVE: they never wait for the issue.
+        const int t = warp - kMmaWarp0;
+        const uint32_t d_tmem = tmem + kColD + 16 * t;
+        const uint32_t a_tmem0 = tmem + kColA + 2 * t * 32;
+        const uint32_t bar_a0 = bar(kBarAEmpty + 2 * t);
+        int cur_tile = -1, since_flush = 0;
+        Ring ring;
+        for (int it = 0; it < len; it++, ring.next()) {
+            bool fresh = it == 0;                               // the first MMA after a drain overwrites D
+            if (it > 0 && (walk.tile != cur_tile || since_flush == kFlushSteps)) { since_flush = 0; fresh = true; }
+            cur_tile = walk.tile;
             since_flush++;
-            mbar_wait(bar(kBarFull + stage), parity);           // weight tile landed
-            const uint32_t wbase = smem_base + stage * kStageBytes + kStepGroups * kChunkBytes;
+            walk.advance();
+            tc_wait(bar(kBarFull + ring.stage), ring.parity);   // the stage's weight tiles have landed
+            const uint32_t wtiles = smem_base + ring.stage * kStageBytes + kStageGroups * kChunkBytes;
 #pragma unroll
-            for (int t = 0; t < kSub; t++) {
-                mbar_wait(bar(kBarAFull + 2 * t + abuf), aparity);
+            for (int half = 0; half < kHalves; half++) {
+                asm volatile("bar.sync %0, 160;" ::"r"(1 + 2 * t + half) : "memory");   // A buffer written, D drained
                 tc_fence_after();
-                const uint32_t a = tmem + kColA + (2 * t + abuf) * 32, d = tmem + kColD + 16 * t;
+                const uint64_t desc = wtile_desc(wtiles + half * kWTileBytes);
 #pragma unroll
                 for (int q = 0; q < kStepGroups; q++)
-                    mma_i8_ts(d, a + 8 * q, wtile_desc(wbase + q * 512), kIdesc, (fresh && q == 0) ? 0u : 1u);
-                mma_commit(bar(kBarAEmpty + 2 * t + abuf));     // A buffer free once these MMAs have read it
+                    mma_i8_ts(d_tmem, a_tmem0 + 32 * half + 8 * q, desc + (uint64_t)(q * (512 >> 4)), kIdesc,
+                              (fresh && half == 0 && q == 0) ? 0u : 1u);
+                mma_commit(bar_a0 + 8 * half);                  // A buffer free once these MMAs have read it
             }
-            mma_commit(bar(kBarEmpty + stage));                 // weight tile free
-            // the accumulators are complete when the next step starts with a flush, or the range ends
-            Cursor nx = c;
-            walk.advance(nx);
-            if (it + 1 == len || nx.tile != c.tile || since_flush == kFlushSteps) mma_commit(bar(kBarDFull));
+            mma_commit(bar(kBarEmpty + ring.stage));            // this sub-tile is done with the stage's weight tiles
+            // the accumulators are complete when the next stage starts with a drain, or the range ends
+            if (it + 1 == len || walk.tile != cur_tile || since_flush == kFlushSteps) mma_commit(bar(kBarDFull + t));
         }
     } else {
-        // ============ expander warps ============
+        // ============ expander warps: sub-tile t = 4 warps = one independent pipeline ============
         const int t = warp >> 2;                                // sub-tile
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;         // this warp's quarter of the TMEM lanes
         const int my = t * 128 + (warp & 3) * 32 + lane;        // sample within the tile
+        const uint32_t d_tmem = tmem + kColD + 16 * t;
+        const uint32_t a_tmem0 = tmem + kColA + 2 * t * 32;     // the sub-tile's two A buffers (32 columns each)
+        const uint32_t bar_a0 = bar(kBarAEmpty + 2 * t);
         double y[K];
 #pragma unroll
         for (int k = 0; k < K; k++) y[k] = 0.0;
@@ -360,19 +404,16 @@ pheno_tc_kernel(const TcParams p)
 #pragma unroll
         for (int k = 0; k < K; k++) escale[k] = p.scale[k].exponent - 6;
         uint32_t dphase = 0;
-        int64_t cur_tile = -1, slot = 0;
-        int since_flush = 0;
+        int cur_tile = -1, since_flush = 0;
+        int64_t slot = 0;
 
-        // read D back, recombine the digits exactly, add to y
+        // read D back (complete once the leader's last commit has fired), recombine the digits exactly, add to y
         auto drain = [&]() {
-            mbar_wait(bar(kBarDFull), dphase);
+            tc_wait(bar(kBarDFull + t), dphase);
             dphase ^= 1u;
             tc_fence_after();
             uint32_t r[16];
-            tmem_ld16(tmem + lane_field + kColD + 16 * t, r);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarDEmpty));
+            tmem_ld16(d_tmem + lane_field, r);
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const long long lo = (long long)(int)r[8 * k] + ((long long)(int)r[8 * k + 1] << 8) + ((long long)(int)r[8 * k + 2] << 16);
@@ -384,58 +425,73 @@ pheno_tc_kernel(const TcParams p)
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 // +=: the rotated walk may visit the tile of its starting point twice (the slots start at 0)
-                p.ypart[(slot * K + k) * p.npad + cur_tile * kTile + my] += y[k];
+                p.ypart[(slot * K + k) * p.npad + (int64_t)cur_tile * kTile + my] += y[k];
                 y[k] = 0.0;
             }
         };
-
-        Cursor c = walk.first;
-        for (int64_t it = 0; it < len; it++, walk.advance(c)) {
-            const int stage = (int)(it % kStages);
-            const uint32_t parity = (uint32_t)((it / kStages) & 1);
-            const uint32_t abuf = (uint32_t)(it & 1), aparity = (uint32_t)((it >> 1) & 1);
-            if (flush_before(it, c.tile, cur_tile, since_flush)) {
-                drain();
-                if (c.tile != cur_tile) store();
-                since_flush = 0;
-            }
-            if (c.tile != cur_tile) {
-                cur_tile = c.tile;
-                slot = cta - cta_of_step(c.tile * p.nblocks, grid, p.steps);
-            }
-            since_flush++;
-
-            mbar_wait(bar(kBarFull + stage), parity);
-            const uint32_t src = smem_base + stage * kStageBytes + my * 4;
-            uint32_t w[kStepGroups];
+        // this thread's 4 words of one half of a stage -> registers
+        auto load_words = [&](uint32_t stage_base, int half, uint32_t (&w)[kStepGroups]) {
+            const uint32_t src = stage_base + half * (kStepGroups * kChunkBytes) + my * 4;
 #pragma unroll
             for (int q = 0; q < kStepGroups; q++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(src + q * kChunkBytes));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarEmpty + stage));                // the words are in registers
+        };
+        // one MMA step of the sub-tile: expand 4 words into the A buffer `half`, hand over to the sub-tile's MMA warp
+        auto mma_step = [&](const uint32_t (&w)[kStepGroups], int half, uint32_t aparity) {
             uint32_t r[32];
 #pragma unroll
             for (int q = 0; q < kStepGroups; q++) {
-                const uint32_t x = w[q], h = x >> 1;
+                const uint32_t x = w[q], hb = __umulhi(x, 0x80000000u);        // x >> 1 on the FMA pipe (the ALU pipe is the limit)
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     r[8 * q + s] = x & (0x03030303u << (2 * s));               // c << 2s
-                    r[8 * q + 4 + s] = x & h & (0x01010101u << (2 * s));       // [c == 3] << 2s
+                    // [c == 3] << 2s = x & (x >> 1) & mask in ONE three-input LOP3
+                    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r[8 * q + 4 + s]) : "r"(x), "r"(hb), "r"(0x01010101u << (2 * s)));
                 }
             }
-            mbar_wait(bar(kBarAEmpty + 2 * t + abuf), aparity ^ 1u);           // the MMAs of step it-2 have read this buffer
+            tc_wait(bar_a0 + 8 * half, aparity ^ 1u);                           // the MMAs of the previous stage have read this buffer
             tc_fence_after();
-            tmem_st32(tmem + lane_field + kColA + (2 * t + abuf) * 32, r);
+            tmem_st32(a_tmem0 + 32 * half + lane_field, r);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
+            asm volatile("bar.arrive %0, 160;" ::"r"(1 + 2 * t + half) : "memory");   // 128 rows are in TMEM (and D was drained)
+        };
+
+        Ring ring;
+        uint32_t w0[kStepGroups], w1[kStepGroups];
+        tc_wait(bar(kBarFull), 0);
+        load_words(smem_base, 0, w0);
+        for (int it = 0; it < len; it++) {
+            const uint32_t stage_base = smem_base + ring.stage * kStageBytes;
+            const uint32_t aparity = (uint32_t)(it & 1);
+            load_words(stage_base, 1, w1);                      // second half of this stage: the stage's words are then all in registers
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarAFull + 2 * t + abuf));
+            if (lane == 0) mbar_arrive(bar(kBarEmpty + ring.stage));
+            if (it > 0 && (walk.tile != cur_tile || since_flush == kFlushSteps)) {
+                drain();
+                if (walk.tile != cur_tile) store();
+                since_flush = 0;
+            }
+            if (walk.tile != cur_tile) {
+                cur_tile = walk.tile;
+                slot = cta - cta_of_step((int64_t)walk.tile * p.nblocks, grid, p.steps);
+            }
+            since_flush++;
+            mma_step(w0, 0, aparity);
+            // the next stage's first half travels while the second half is expanded
+            ring.next();
+            walk.advance();
+            if (it + 1 < len) {
+                tc_wait(bar(kBarFull + ring.stage), ring.parity);
+                load_words(smem_base + ring.stage * kStageBytes, 0, w0);
+            }
+            mma_step(w1, 1, aparity);
         }
         drain();
         store();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kExpWarps + 1) tmem_dealloc(tmem, kTmemCols);
+    if (warp == kProducerWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 // y[k][i] = C_k + sum over the slots of the tile that holds sample i, in slot order
@@ -455,20 +511,46 @@ tc_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int 
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// the panel as a 2-D tensor for the TMA: dimension 0 = 8-byte elements (2 samples) of a group, dimension 1 = groups
+int make_panel_map(simu_b200_ctx *ctx, CUtensorMap *map)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+            return ctx_fail(ctx, SIMU_B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)(ctx->s16_stride / 8), (cuuint64_t)((ctx->panel_rows + 15) / 16)};
+    const cuuint64_t strides[1] = {(cuuint64_t)ctx->s16_stride};
+    const cuuint32_t box[2] = {(cuuint32_t)(kTile / 2), (cuuint32_t)kStageGroups};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, ctx->panel, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ctx_fail(ctx, SIMU_B200_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SIMU_B200_OK;
+}
+
 template <int K>
 int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2, double *d_y1,
            double *d_y2)
 {
     const int64_t n = ctx->n_samples;
     const int64_t tiles = (n + kTile - 1) / kTile;
-    const int64_t nblocks = (mc + kStepSnps - 1) / kStepSnps;
+    const int64_t nblocks = (mc + kStageSnps - 1) / kStageSnps;
     const int64_t steps = tiles * nblocks;
     const int64_t grid = steps < ctx->num_sms ? steps : ctx->num_sms;
     const int slots = (int)((grid + tiles - 1) / tiles) + 1;
     const int64_t npad = tiles * kTile;
 
     // weight tiles, then: [TcScale x 2][ticket + pad][partials 4 x kPrepBlocks doubles]
-    const size_t wt_bytes = (size_t)nblocks * kWTileBytes;
+    const size_t wt_bytes = (size_t)nblocks * kHalves * kWTileBytes;
     const size_t aux_off = (wt_bytes + 255) & ~(size_t)255;
     uint8_t *wt = (uint8_t *)ctx_scratch(ctx, SCR_TCW, aux_off + 64 + 4 * kPrepBlocks * sizeof(double));
     const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
@@ -482,18 +564,21 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
         CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         ctx->tc_attr_set = true;
     }
+    CUtensorMap map;
+    int rc = make_panel_map(ctx, &map);
+    if (rc) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
     int ps = prof_begin(ctx, PROF_LUT_BUILD);
     tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);
-    tc_weights_kernel<K><<<(unsigned)nblocks, 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, scale, wt);
+    tc_weights_kernel<K><<<(unsigned)(nblocks * kHalves), 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, scale, wt);
     prof_end(ctx, ps);
 
     TcParams p;
     p.panel = ctx->panel; p.s16_stride = ctx->s16_stride; p.mc = mc; p.n_samples = n; p.wt = wt; p.scale = scale;
     p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
     ps = prof_begin(ctx, PROF_LUT_MAIN);
-    pheno_tc_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p);
+    pheno_tc_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p, map);
     prof_end(ctx, ps);
     ps = prof_begin(ctx, PROF_LUT_REDUCE);
     tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2);

@@ -289,6 +289,111 @@ __global__ void __launch_bounds__(256) probe_issue_u(long long *out, int iters, 
     if (warp == 0) tmem_dealloc(tm, 512);
 }
 
+
+// latencies of the synchronisation primitives the kernel is made of, one warp, 512 repetitions each (clk per op)
+__global__ void __launch_bounds__(128) probe_lat(long long *out)
+{
+    __shared__ __align__(1024) uint8_t bs[8192];
+    __shared__ __align__(8) uint64_t bar[4];
+    __shared__ uint32_t tbase;
+    const int t = threadIdx.x, lane = t & 31;
+    const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+    for (int i = t; i < 8192; i += blockDim.x) bs[i] = (uint8_t)(i & 3);
+    if (t == 0) { for (int i = 0; i < 4; i++) mbar_init(smem_u32(&bar[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) tmem_alloc(smem_u32(&tbase), 512);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = tbase;
+    const uint32_t lane_base = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    const int R = 512;
+    uint32_t r[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) r[c] = t * 131 + c;
+    long long t0, t1;
+    // (0) try_wait on a barrier whose phase already completed (parity 1 of a fresh barrier)
+    t0 = clock64();
+    for (int i = 0; i < R; i++) mbar_wait(smem_u32(&bar[1]), 1);
+    t1 = clock64();
+    if (t == 0) out[0] = (t1 - t0) / R;
+    // (1) st.x32 + wait::st
+    t0 = clock64();
+    for (int i = 0; i < R; i++) { st32(lane_base + 256, r); wait_st(); }
+    t1 = clock64();
+    if (t == 0) out[1] = (t1 - t0) / R;
+    // (2) fence::before + fence::after pair
+    t0 = clock64();
+    for (int i = 0; i < R; i++) { fence_before(); fence_after(); }
+    t1 = clock64();
+    if (t == 0) out[2] = (t1 - t0) / R;
+    // (3) bar.sync of 128 threads
+    __syncthreads();
+    t0 = clock64();
+    for (int i = 0; i < R; i++) asm volatile("bar.sync 1, 128;" ::: "memory");
+    t1 = clock64();
+    if (t == 0) out[3] = (t1 - t0) / R;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc_i8(128, 16, 0, 1);
+        const uint64_t bd = make_bdesc(smem_u32(bs), 256, 128);
+        // (4) commit alone -> wait for its arrival
+        uint32_t ph = 0;
+        t0 = clock64();
+        for (int i = 0; i < R; i++) {
+            asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(&bar[0])) : "memory");
+            mbar_wait(smem_u32(&bar[0]), ph); ph ^= 1;
+        }
+        t1 = clock64();
+        if (lane == 0) out[4] = (t1 - t0) / R;
+        // (5) 4 MMAs + commit -> wait for the arrival (issue + execution + signalling latency)
+        t0 = clock64();
+        for (int i = 0; i < R; i++) {
+            mma_i8_ts_elect(tm, tm + 256, bd, idesc, 1); mma_i8_ts_elect(tm, tm + 264, bd + 32, idesc, 1);
+            mma_i8_ts_elect(tm, tm + 272, bd + 64, idesc, 1); mma_i8_ts_elect(tm, tm + 280, bd + 96, idesc, 1);
+            asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(&bar[0])) : "memory");
+            mbar_wait(smem_u32(&bar[0]), ph); ph ^= 1;
+        }
+        t1 = clock64();
+        if (lane == 0) out[5] = (t1 - t0) / R;
+        // (6) issue cost alone: 4 MMAs + commit, no wait (one wait at the end)
+        t0 = clock64();
+        for (int i = 0; i < R; i++) {
+            mma_i8_ts_elect(tm, tm + 256, bd, idesc, 1); mma_i8_ts_elect(tm, tm + 264, bd + 32, idesc, 1);
+            mma_i8_ts_elect(tm, tm + 272, bd + 64, idesc, 1); mma_i8_ts_elect(tm, tm + 280, bd + 96, idesc, 1);
+            asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(&bar[2])) : "memory");
+        }
+        t1 = clock64();
+        if (lane == 0) out[6] = (t1 - t0) / R;
+        // (7) mbarrier.arrive (count 1) + try_wait on it: software signalling round trip inside a warp
+        t0 = clock64();
+        uint32_t ph3 = 0;
+        for (int i = 0; i < R; i++) {
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[3])) : "memory");
+            mbar_wait(smem_u32(&bar[3]), ph3); ph3 ^= 1;
+        }
+        t1 = clock64();
+        if (lane == 0) out[7] = (t1 - t0) / R;
+        // (8) 4 x ld.shared.u32 dependent use
+        t0 = clock64();
+        uint32_t acc = 0;
+        for (int i = 0; i < R; i++) {
+            uint32_t a, b, c, d;
+            const uint32_t src = smem_u32(bs) + ((lane * 4 + (acc & 3) * 128) & 8191);
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a) : "r"(src));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b) : "r"(src + 2048));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(src + 4096));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(src + 6144));
+            acc += a + b + c + d;
+        }
+        t1 = clock64();
+        if (lane == 0) { out[8] = (t1 - t0) / R; out[15] = acc; }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 512);
+}
+
 static int run_case(int n, int nmma, int swap)
 {
     const int kb = 32 * nmma;
@@ -360,6 +465,17 @@ int main(int argc, char **argv)
                     printf("issue N=%d issuers=%d same_acc=%d: %.2f clk per MMA overall (%.2f clk per MMA per issuer to issue)\n", n, issuers, same,
                            h[0] / (4096.0 * issuers), h[2] / 4096.0);
                 }
+    }
+    if (!strcmp(what, "lat") || !strcmp(what, "all")) {
+        long long *d, h[16];
+        CK(cudaMalloc(&d, 128));
+        probe_lat<<<1, 128>>>(d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("lat failed: %s\n", cudaGetErrorString(e)); return 1; }
+        CK(cudaMemcpy(h, d, 128, cudaMemcpyDeviceToHost));
+        printf("latency (clk): try_wait(complete) %lld | st.x32+wait::st %lld | fence before+after %lld | bar.sync(128) %lld | commit->arrival %lld | "
+               "4 MMA+commit->arrival %lld | 4 MMA+commit issue only %lld | arrive+try_wait %lld | 4 LDS+use %lld\n",
+               h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
     }
     if (!strcmp(what, "issueu") || !strcmp(what, "all")) {
         long long *d, h[8];
