@@ -45,30 +45,33 @@
 
 namespace {
 
-constexpr int kTile = 512;                          // samples per CTA tile
-constexpr int kSub = 4;                             // 128-sample sub-tiles (one TMEM lane set each)
-constexpr int kStepGroups = 4;                      // 16-SNP groups per MMA step (one A buffer)
-constexpr int kStepSnps = 16 * kStepGroups;         // 64
-constexpr int kHalves = 2;                          // MMA steps per shared-memory stage
-constexpr int kStageGroups = kHalves * kStepGroups; // 8 groups = 128 SNPs per stage: ONE tensor copy
+constexpr int kSub = 6;                             // 128-sample sub-tiles (one TMEM lane set each)
+constexpr int kTile = 128 * kSub;                   // 768 samples per CTA tile
+constexpr int kStepGroups = 4;                      // 16-SNP groups per tcgen05.st (32 TMEM columns)
+constexpr int kHalves = 2;                          // ... and per shared-memory stage / A buffer
+constexpr int kStageGroups = kHalves * kStepGroups; // 8 groups = 128 SNPs per stage
+constexpr int kStepSnps = 16 * kStepGroups;         // 64: one weight tile
 constexpr int kStageSnps = 16 * kStageGroups;       // 128
-constexpr int kExpWarps = 4 * kSub;                 // 16
+constexpr int kExpWarps = 4 * kSub;                 // 24
 constexpr int kMmaWarp0 = kExpWarps;                // one MMA-issuing warp per sub-tile
 constexpr int kProducerWarp = kExpWarps + kSub;
-constexpr int kThreads = (kExpWarps + kSub + 1) * 32;
-constexpr int kChunkBytes = kTile * 4;              // one group's words for the tile
+constexpr int kThreads = (kExpWarps + kSub + 1) * 32;      // 31 warps
+constexpr int kBoxSamples = kTile / 2;              // a tensor copy: 384 samples (192 8-byte elements <= 256) x 8 groups
+constexpr int kBoxRowBytes = kBoxSamples * 4;       // 1536
+constexpr int kBoxBytes = kStageGroups * kBoxRowBytes;      // 12 KB
 constexpr int kWTileBytes = kStepGroups * 512;      // weights of 64 SNPs: 4 x [N = 16][K = 32] s8
-constexpr int kStageBytes = kStageGroups * kChunkBytes + kHalves * kWTileBytes;   // 16 KB + 4 KB
-constexpr int kStages = 6;                          // 120 KB: also keeps a second CTA (and its TMEM request) off the SM
+constexpr int kStageBytes = 2 * kBoxBytes + kHalves * kWTileBytes;     // 24 KB + 4 KB
+constexpr int kStages = 5;                          // 140 KB: also keeps a second CTA (and its TMEM request) off the SM
 constexpr int kFlushSteps = 128;                    // stages between drains: 16384 SNPs, |D| < 2^29
 constexpr int kDigits = 6;                          // signed base-256 digits per weight (of 8 columns per trait)
 constexpr int kFracBits = 40;                       // |W| / 2^e < 2^40
 constexpr int kTmemCols = 512;
 constexpr int kColD = 0;                            // D: kSub x 16 columns
-constexpr int kColA = 64;                           // A: kSub x 2 buffers x 32 columns
+constexpr int kColA = 16 * kSub;                    // A: kSub x 64 columns (one buffer per sub-tile = one stage)
+static_assert(kColA + 64 * kSub <= kTmemCols, "TMEM columns");
 // barriers (8 bytes each) after the ring
 constexpr int kBarFull = 0, kBarEmpty = kBarFull + kStages, kBarAEmpty = kBarEmpty + kStages,
-              kBarDFull = kBarAEmpty + 2 * kSub, kNumBars = kBarDFull + kSub;
+              kBarDFull = kBarAEmpty + kSub, kNumBars = kBarDFull + kSub;
 constexpr int kSmemBytes = kStages * kStageBytes + kNumBars * 8 + 16;
 
 // ------------------------------------------------------------------ tcgen05 wrappers
@@ -325,8 +328,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(bar(kBarFull + s), 1); mbar_init(bar(kBarEmpty + s), kExpWarps + kSub); }
-        for (int i = 0; i < 2 * kSub; i++) mbar_init(bar(kBarAEmpty + i), 1);
-        for (int i = 0; i < kSub; i++) mbar_init(bar(kBarDFull + i), 1);
+        for (int i = 0; i < kSub; i++) { mbar_init(bar(kBarAEmpty + i), 1); mbar_init(bar(kBarDFull + i), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kProducerWarp) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -350,8 +352,10 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
             if (lane == 0) {
                 mbar_wait_backoff(bar(kBarEmpty + ring.stage), ring.parity ^ 1u);
                 mbar_arrive_expect_tx(bar(kBarFull + ring.stage), (uint32_t)kStageBytes);
-                tensor_g2s(stage_base, &panel_map, walk.tile * (kTile / 2), walk.blk * kStageGroups, bar(kBarFull + ring.stage), pol_stream);
-                bulk_g2s(stage_base + kStageGroups * kChunkBytes, p.wt + (int64_t)walk.blk * (kHalves * kWTileBytes), kHalves * kWTileBytes,
+                const int x = walk.tile * (kTile / 2), y = walk.blk * kStageGroups;
+                tensor_g2s(stage_base, &panel_map, x, y, bar(kBarFull + ring.stage), pol_stream);
+                tensor_g2s(stage_base + kBoxBytes, &panel_map, x + kBoxSamples / 2, y, bar(kBarFull + ring.stage), pol_stream);
+                bulk_g2s(stage_base + 2 * kBoxBytes, p.wt + (int64_t)walk.blk * (kHalves * kWTileBytes), kHalves * kWTileBytes,
                          bar(kBarFull + ring.stage), pol_keep);
             }
             __syncwarp();
@@ -362,8 +366,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         // barrier of 160 threads on which the 128 expander threads only ARRIVE: they never wait for the issue.
         const int t = warp - kMmaWarp0;
         const uint32_t d_tmem = tmem + kColD + 16 * t;
-        const uint32_t a_tmem0 = tmem + kColA + 2 * t * 32;
-        const uint32_t bar_a0 = bar(kBarAEmpty + 2 * t);
+        const uint32_t a_tmem = tmem + kColA + 64 * t;
         int cur_tile = -1, since_flush = 0;
         Ring ring;
         for (int it = 0; it < len; it++, ring.next()) {
@@ -373,18 +376,13 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
             since_flush++;
             walk.advance();
             tc_wait(bar(kBarFull + ring.stage), ring.parity);   // the stage's weight tiles have landed
-            const uint32_t wtiles = smem_base + ring.stage * kStageBytes + kStageGroups * kChunkBytes;
+            const uint64_t desc = wtile_desc(smem_base + ring.stage * kStageBytes + 2 * kBoxBytes);
+            asm volatile("bar.sync %0, 160;" ::"r"(1 + t) : "memory");             // A buffer written, D drained
+            tc_fence_after();
 #pragma unroll
-            for (int half = 0; half < kHalves; half++) {
-                asm volatile("bar.sync %0, 160;" ::"r"(1 + 2 * t + half) : "memory");   // A buffer written, D drained
-                tc_fence_after();
-                const uint64_t desc = wtile_desc(wtiles + half * kWTileBytes);
-#pragma unroll
-                for (int q = 0; q < kStepGroups; q++)
-                    mma_i8_ts(d_tmem, a_tmem0 + 32 * half + 8 * q, desc + (uint64_t)(q * (512 >> 4)), kIdesc,
-                              (fresh && half == 0 && q == 0) ? 0u : 1u);
-                mma_commit(bar_a0 + 8 * half);                  // A buffer free once these MMAs have read it
-            }
+            for (int q = 0; q < kStageGroups; q++)
+                mma_i8_ts(d_tmem, a_tmem + 8 * q, desc + (uint64_t)(q * (512 >> 4)), kIdesc, (fresh && q == 0) ? 0u : 1u);
+            mma_commit(bar(kBarAEmpty + t));                    // A buffer free once these MMAs have read it
             mma_commit(bar(kBarEmpty + ring.stage));            // this sub-tile is done with the stage's weight tiles
             // the accumulators are complete when the next stage starts with a drain, or the range ends
             if (it + 1 == len || walk.tile != cur_tile || since_flush == kFlushSteps) mma_commit(bar(kBarDFull + t));
@@ -395,15 +393,16 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;         // this warp's quarter of the TMEM lanes
         const int my = t * 128 + (warp & 3) * 32 + lane;        // sample within the tile
         const uint32_t d_tmem = tmem + kColD + 16 * t;
-        const uint32_t a_tmem0 = tmem + kColA + 2 * t * 32;     // the sub-tile's two A buffers (32 columns each)
-        const uint32_t bar_a0 = bar(kBarAEmpty + 2 * t);
+        const uint32_t a_tmem = tmem + kColA + 64 * t + lane_field;   // the sub-tile's A buffer: 64 columns = one stage
+        // this thread's word in a stage: box (384 samples) x group row (1536 B) x sample
+        const uint32_t my_off = (uint32_t)((my / kBoxSamples) * kBoxBytes + (my % kBoxSamples) * 4);
         double y[K];
 #pragma unroll
         for (int k = 0; k < K; k++) y[k] = 0.0;
         int escale[K];
 #pragma unroll
         for (int k = 0; k < K; k++) escale[k] = p.scale[k].exponent - 6;
-        uint32_t dphase = 0;
+        uint32_t dphase = 0, aphase = 0;
         int cur_tile = -1, since_flush = 0;
         int64_t slot = 0;
 
@@ -431,12 +430,12 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         };
         // this thread's 4 words of one half of a stage -> registers
         auto load_words = [&](uint32_t stage_base, int half, uint32_t (&w)[kStepGroups]) {
-            const uint32_t src = stage_base + half * (kStepGroups * kChunkBytes) + my * 4;
+            const uint32_t src = stage_base + my_off + half * (kStepGroups * kBoxRowBytes);
 #pragma unroll
-            for (int q = 0; q < kStepGroups; q++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(src + q * kChunkBytes));
+            for (int q = 0; q < kStepGroups; q++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(src + q * kBoxRowBytes));
         };
-        // one MMA step of the sub-tile: expand 4 words into the A buffer `half`, hand over to the sub-tile's MMA warp
-        auto mma_step = [&](const uint32_t (&w)[kStepGroups], int half, uint32_t aparity) {
+        // expand 4 words (64 SNPs) into 32 columns of the A buffer
+        auto expand_store = [&](const uint32_t (&w)[kStepGroups], int half) {
             uint32_t r[32];
 #pragma unroll
             for (int q = 0; q < kStepGroups; q++) {
@@ -448,12 +447,11 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                     asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r[8 * q + 4 + s]) : "r"(x), "r"(hb), "r"(0x01010101u << (2 * s)));
                 }
             }
-            tc_wait(bar_a0 + 8 * half, aparity ^ 1u);                           // the MMAs of the previous stage have read this buffer
-            tc_fence_after();
-            tmem_st32(a_tmem0 + 32 * half + lane_field, r);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            asm volatile("bar.arrive %0, 160;" ::"r"(1 + 2 * t + half) : "memory");   // 128 rows are in TMEM (and D was drained)
+            if (half == 0) {
+                tc_wait(bar(kBarAEmpty + t), aphase ^ 1u);       // the MMAs of the previous stage have read the buffer
+                tc_fence_after();
+            }
+            tmem_st32(a_tmem + 32 * half, r);
         };
 
         Ring ring;
@@ -461,9 +459,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         tc_wait(bar(kBarFull), 0);
         load_words(smem_base, 0, w0);
         for (int it = 0; it < len; it++) {
-            const uint32_t stage_base = smem_base + ring.stage * kStageBytes;
-            const uint32_t aparity = (uint32_t)(it & 1);
-            load_words(stage_base, 1, w1);                      // second half of this stage: the stage's words are then all in registers
+            load_words(smem_base + ring.stage * kStageBytes, 1, w1);       // the stage's words are then all in registers
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(kBarEmpty + ring.stage));
             if (it > 0 && (walk.tile != cur_tile || since_flush == kFlushSteps)) {
@@ -476,7 +472,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                 slot = cta - cta_of_step((int64_t)walk.tile * p.nblocks, grid, p.steps);
             }
             since_flush++;
-            mma_step(w0, 0, aparity);
+            expand_store(w0, 0);
             // the next stage's first half travels while the second half is expanded
             ring.next();
             walk.advance();
@@ -484,7 +480,11 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                 tc_wait(bar(kBarFull + ring.stage), ring.parity);
                 load_words(smem_base + ring.stage * kStageBytes, 0, w0);
             }
-            mma_step(w1, 1, aparity);
+            expand_store(w1, 1);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            asm volatile("bar.arrive %0, 160;" ::"r"(1 + t) : "memory");   // the sub-tile's 128 rows x 128 SNPs are in TMEM (and D was drained)
+            aphase ^= 1u;
         }
         drain();
         store();
@@ -529,7 +529,7 @@ int make_panel_map(simu_b200_ctx *ctx, CUtensorMap *map)
     }
     const cuuint64_t dims[2] = {(cuuint64_t)(ctx->s16_stride / 8), (cuuint64_t)((ctx->panel_rows + 15) / 16)};
     const cuuint64_t strides[1] = {(cuuint64_t)ctx->s16_stride};
-    const cuuint32_t box[2] = {(cuuint32_t)(kTile / 2), (cuuint32_t)kStageGroups};
+    const cuuint32_t box[2] = {(cuuint32_t)(kBoxSamples / 2), (cuuint32_t)kStageGroups};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, ctx->panel, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
