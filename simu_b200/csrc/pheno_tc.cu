@@ -89,13 +89,16 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem], issued by one elected lane of a converged warp (operands warp-uniform)
-__device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a, uint32_t bdesc_lo, uint32_t bdesc_hi, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
-        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-        ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 bd, {%2, %3};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], bd, %4, {%6, %7, %8, %9}, p;\n\t}"
+        ::"r"(d), "r"(a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
 }
+// keep a value in a register: without this the compiler re-derives shared-memory addresses (S2UR + ULEA + UIADD3 ...)
+// at every use, which was a quarter of all issued instructions
+__device__ __forceinline__ uint32_t pin(uint32_t x) { asm volatile("" : "+r"(x)); return x; }
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint32_t bar)
 {
@@ -126,6 +129,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 // the warp reconverge behind it was measured 50 % SLOWER than all lanes polling.)
 __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity)
 {
+#pragma unroll 1
     for (int i = 0; i < (1 << 22); i++)
         if (mbar_test(bar, parity)) return;
     __trap();
@@ -133,10 +137,8 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity)
 
 // shared-memory matrix descriptor of one weight sub-tile: [N = 16][K = 32] s8, K-major, no swizzle, as 8 x 16-byte
 // core matrices: K chunks 256 B apart (leading-dimension byte offset), 8-column groups 128 B apart (stride)
-__device__ __forceinline__ uint64_t wtile_desc(uint32_t saddr)
-{
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(256u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
-}
+__device__ __forceinline__ uint32_t wtile_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((256u >> 4) << 16); }
+constexpr uint32_t kWtileDescHi = (128u >> 4) | (1u << 14);
 // one box of the panel's tensor map (256 x 8-byte elements = 512 samples, kStageGroups rows) -> shared memory
 __device__ __forceinline__ void tensor_g2s(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar, uint64_t policy)
 {
@@ -305,6 +307,26 @@ struct Walk32 {
     }
 };
 
+// A maximal run of stages that needs no bookkeeping inside: one sample tile, consecutive SNP blocks, no drain.
+// Every run ends with a drain of the accumulators (tile end, wrap of the rotated walk, or kFlushSteps stages).
+struct Segment { int tile, blk, n; };
+
+struct SegWalk {
+    Walk32 w;
+    int done = 0;
+    __device__ __forceinline__ SegWalk(int64_t steps, int64_t nblocks, int64_t cta, int64_t grid) : w(steps, nblocks, cta, grid) {}
+    __device__ __forceinline__ bool next(Segment &s)
+    {
+        if (done == w.len) return false;
+        s.tile = w.tile; s.blk = w.blk;
+        s.n = min(min(w.nb - w.blk, w.left), min(kFlushSteps, w.len - done));
+        w.blk += s.n; w.left -= s.n; done += s.n;
+        if (w.blk == w.nb) { w.blk = 0; w.tile++; }
+        if (w.left == 0) { w.tile = w.tile_b; w.blk = w.blk_b; w.left = w.len; }
+        return true;
+    }
+};
+
 struct Ring {                       // position in the shared-memory ring
     int stage = 0;
     uint32_t parity = 0;
@@ -319,11 +341,11 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);      // warp-uniform for the compiler
     const int64_t grid = gridDim.x, cta = blockIdx.x;
-    Walk32 walk(p.steps, p.nblocks, cta, grid);
-    const int len = walk.len;
+    SegWalk walk(p.steps, p.nblocks, cta, grid);
+    const int len = walk.w.len;
 
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bars = smem_base + kStages * kStageBytes;
+    const uint32_t smem_base = pin(smem_u32(smem));
+    const uint32_t bars = pin(smem_base + kStages * kStageBytes);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kStages * kStageBytes + kNumBars * 8);
     auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
     if (threadIdx.x == 0) {
@@ -335,31 +357,34 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = pin(*tmem_slot);
+    Segment seg;
 
     if (warp == kProducerWarp) {
-        // ============ producer warp: per stage ONE tensor copy (8 groups x 2 KB of words; rows and columns
-        // beyond the panel arrive as zeros) and one 4 KB bulk copy of the stage's weight tiles.  A bulk copy
-        // costs its issuing warp ~200 clk whatever its size (measured: five 2 KB copies per 64 SNPs made
+        // ============ producer warp: per stage two tensor copies (384 samples x 8 groups of words each; rows and
+        // columns beyond the panel arrive as zeros) and one 4 KB bulk copy of the stage's weight tiles.  A bulk
+        // copy costs its issuing warp ~200 clk whatever its size (measured: five 2 KB copies per 64 SNPs made
         // this warp the bottleneck at 1024 clk per step), so the copies are few and large.
         uint64_t pol_stream, pol_keep;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&panel_map) : "memory");
-        Ring ring;
-        for (int it = 0; it < len; it++, walk.advance(), ring.next()) {
-            const uint32_t stage_base = smem_base + ring.stage * kStageBytes;
-            if (lane == 0) {
-                mbar_wait_backoff(bar(kBarEmpty + ring.stage), ring.parity ^ 1u);
-                mbar_arrive_expect_tx(bar(kBarFull + ring.stage), (uint32_t)kStageBytes);
-                const int x = walk.tile * (kTile / 2), y = walk.blk * kStageGroups;
-                tensor_g2s(stage_base, &panel_map, x, y, bar(kBarFull + ring.stage), pol_stream);
-                tensor_g2s(stage_base + kBoxBytes, &panel_map, x + kBoxSamples / 2, y, bar(kBarFull + ring.stage), pol_stream);
-                bulk_g2s(stage_base + 2 * kBoxBytes, p.wt + (int64_t)walk.blk * (kHalves * kWTileBytes), kHalves * kWTileBytes,
-                         bar(kBarFull + ring.stage), pol_keep);
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&panel_map) : "memory");
+            Ring ring;
+            while (walk.next(seg)) {
+                const int x = seg.tile * (kTile / 2);
+                for (int i = 0; i < seg.n; i++, ring.next()) {
+                    const uint32_t stage_base = smem_base + ring.stage * kStageBytes, full = bar(kBarFull + ring.stage);
+                    const int blk = seg.blk + i;
+                    mbar_wait_backoff(bar(kBarEmpty + ring.stage), ring.parity ^ 1u);
+                    mbar_arrive_expect_tx(full, (uint32_t)kStageBytes);
+                    tensor_g2s(stage_base, &panel_map, x, blk * kStageGroups, full, pol_stream);
+                    tensor_g2s(stage_base + kBoxBytes, &panel_map, x + kBoxSamples / 2, blk * kStageGroups, full, pol_stream);
+                    bulk_g2s(stage_base + 2 * kBoxBytes, p.wt + (int64_t)blk * (kHalves * kWTileBytes), kHalves * kWTileBytes, full, pol_keep);
+                }
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else if (warp >= kMmaWarp0) {
         // ============ MMA warps: warp kMmaWarp0 + t serves sub-tile t.  The whole warp runs the loop (uniform
         // operands -> uniform registers), one elected lane issues.  The hand-over from the expanders is a named
@@ -367,35 +392,32 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         const int t = warp - kMmaWarp0;
         const uint32_t d_tmem = tmem + kColD + 16 * t;
         const uint32_t a_tmem = tmem + kColA + 64 * t;
-        int cur_tile = -1, since_flush = 0;
+        const uint32_t bar_aempty = bar(kBarAEmpty + t), bar_dfull = bar(kBarDFull + t);
         Ring ring;
-        for (int it = 0; it < len; it++, ring.next()) {
-            bool fresh = it == 0;                               // the first MMA after a drain overwrites D
-            if (it > 0 && (walk.tile != cur_tile || since_flush == kFlushSteps)) { since_flush = 0; fresh = true; }
-            cur_tile = walk.tile;
-            since_flush++;
-            walk.advance();
-            tc_wait(bar(kBarFull + ring.stage), ring.parity);   // the stage's weight tiles have landed
-            const uint64_t desc = wtile_desc(smem_base + ring.stage * kStageBytes + 2 * kBoxBytes);
-            asm volatile("bar.sync %0, 160;" ::"r"(1 + t) : "memory");             // A buffer written, D drained
-            tc_fence_after();
+        while (walk.next(seg)) {
+            for (int i = 0; i < seg.n; i++, ring.next()) {
+                tc_wait(bar(kBarFull + ring.stage), ring.parity);       // the stage's weight tiles have landed
+                const uint32_t desc = wtile_desc_lo(smem_base + ring.stage * kStageBytes + 2 * kBoxBytes);
+                asm volatile("bar.sync %0, 160;" ::"r"(1 + t) : "memory");     // A buffer written, D drained
+                tc_fence_after();
 #pragma unroll
-            for (int q = 0; q < kStageGroups; q++)
-                mma_i8_ts(d_tmem, a_tmem + 8 * q, desc + (uint64_t)(q * (512 >> 4)), kIdesc, (fresh && q == 0) ? 0u : 1u);
-            mma_commit(bar(kBarAEmpty + t));                    // A buffer free once these MMAs have read it
-            mma_commit(bar(kBarEmpty + ring.stage));            // this sub-tile is done with the stage's weight tiles
-            // the accumulators are complete when the next stage starts with a drain, or the range ends
-            if (it + 1 == len || walk.tile != cur_tile || since_flush == kFlushSteps) mma_commit(bar(kBarDFull + t));
+                for (int q = 0; q < kStageGroups; q++)      // the first MMA of a segment overwrites D
+                    mma_i8_ts(d_tmem, a_tmem + 8 * q, desc + q * (512 >> 4), kWtileDescHi, kIdesc, (i == 0 && q == 0) ? 0u : 1u);
+                mma_commit(bar_aempty);                      // A buffer free once these MMAs have read it
+                mma_commit(bar(kBarEmpty + ring.stage));    // this sub-tile is done with the stage's weight tiles
+            }
+            mma_commit(bar_dfull);                           // the segment's accumulators are complete
         }
     } else {
         // ============ expander warps: sub-tile t = 4 warps = one independent pipeline ============
         const int t = warp >> 2;                                // sub-tile
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;         // this warp's quarter of the TMEM lanes
         const int my = t * 128 + (warp & 3) * 32 + lane;        // sample within the tile
-        const uint32_t d_tmem = tmem + kColD + 16 * t;
+        const uint32_t d_tmem = tmem + kColD + 16 * t + lane_field;
         const uint32_t a_tmem = tmem + kColA + 64 * t + lane_field;   // the sub-tile's A buffer: 64 columns = one stage
+        const uint32_t bar_aempty = bar(kBarAEmpty + t), bar_dfull = bar(kBarDFull + t);
         // this thread's word in a stage: box (384 samples) x group row (1536 B) x sample
-        const uint32_t my_off = (uint32_t)((my / kBoxSamples) * kBoxBytes + (my % kBoxSamples) * 4);
+        const uint32_t my_off = pin(smem_base + (uint32_t)((my / kBoxSamples) * kBoxBytes + (my % kBoxSamples) * 4));
         double y[K];
 #pragma unroll
         for (int k = 0; k < K; k++) y[k] = 0.0;
@@ -403,16 +425,14 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 #pragma unroll
         for (int k = 0; k < K; k++) escale[k] = p.scale[k].exponent - 6;
         uint32_t dphase = 0, aphase = 0;
-        int cur_tile = -1, since_flush = 0;
-        int64_t slot = 0;
 
-        // read D back (complete once the leader's last commit has fired), recombine the digits exactly, add to y
+        // read D back (complete once the MMA warp's commit has fired), recombine the digits exactly, add to y
         auto drain = [&]() {
-            tc_wait(bar(kBarDFull + t), dphase);
+            tc_wait(bar_dfull, dphase);
             dphase ^= 1u;
             tc_fence_after();
             uint32_t r[16];
-            tmem_ld16(d_tmem + lane_field, r);
+            tmem_ld16(d_tmem, r);
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 const long long lo = (long long)(int)r[8 * k] + ((long long)(int)r[8 * k + 1] << 8) + ((long long)(int)r[8 * k + 2] << 16);
@@ -420,17 +440,18 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                 y[k] += ldexp((double)hi * 16777216.0 + (double)lo, escale[k]);
             }
         };
-        auto store = [&]() {
+        auto store = [&](int tile) {
+            const int64_t slot = cta - cta_of_step((int64_t)tile * p.nblocks, grid, p.steps);
 #pragma unroll
             for (int k = 0; k < K; k++) {
                 // +=: the rotated walk may visit the tile of its starting point twice (the slots start at 0)
-                p.ypart[(slot * K + k) * p.npad + (int64_t)cur_tile * kTile + my] += y[k];
+                p.ypart[(slot * K + k) * p.npad + (int64_t)tile * kTile + my] += y[k];
                 y[k] = 0.0;
             }
         };
         // this thread's 4 words of one half of a stage -> registers
-        auto load_words = [&](uint32_t stage_base, int half, uint32_t (&w)[kStepGroups]) {
-            const uint32_t src = stage_base + my_off + half * (kStepGroups * kBoxRowBytes);
+        auto load_words = [&](int stage, int half, uint32_t (&w)[kStepGroups]) {
+            const uint32_t src = my_off + stage * kStageBytes + half * (kStepGroups * kBoxRowBytes);
 #pragma unroll
             for (int q = 0; q < kStepGroups; q++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(src + q * kBoxRowBytes));
         };
@@ -448,7 +469,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                 }
             }
             if (half == 0) {
-                tc_wait(bar(kBarAEmpty + t), aphase ^ 1u);       // the MMAs of the previous stage have read the buffer
+                tc_wait(bar_aempty, aphase ^ 1u);                // the MMAs of the previous stage have read the buffer
                 tc_fence_after();
             }
             tmem_st32(a_tmem + 32 * half, r);
@@ -456,38 +477,35 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 
         Ring ring;
         uint32_t w0[kStepGroups], w1[kStepGroups];
+        int remaining = len, prev_tile = -1;
         tc_wait(bar(kBarFull), 0);
-        load_words(smem_base, 0, w0);
-        for (int it = 0; it < len; it++) {
-            load_words(smem_base + ring.stage * kStageBytes, 1, w1);       // the stage's words are then all in registers
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarEmpty + ring.stage));
-            if (it > 0 && (walk.tile != cur_tile || since_flush == kFlushSteps)) {
+        load_words(0, 0, w0);
+        while (walk.next(seg)) {
+            if (prev_tile >= 0) {                               // the previous segment's sums
                 drain();
-                if (walk.tile != cur_tile) store();
-                since_flush = 0;
+                if (seg.tile != prev_tile) store(prev_tile);
             }
-            if (walk.tile != cur_tile) {
-                cur_tile = walk.tile;
-                slot = cta - cta_of_step((int64_t)walk.tile * p.nblocks, grid, p.steps);
+            prev_tile = seg.tile;
+            for (int i = 0; i < seg.n; i++) {
+                load_words(ring.stage, 1, w1);                  // the stage's words are then all in registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarEmpty + ring.stage));
+                expand_store(w0, 0);
+                // the next stage's first half travels while the second half is expanded
+                ring.next();
+                if (--remaining > 0) {
+                    tc_wait(bar(kBarFull + ring.stage), ring.parity);
+                    load_words(ring.stage, 0, w0);
+                }
+                expand_store(w1, 1);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                asm volatile("bar.arrive %0, 160;" ::"r"(1 + t) : "memory");   // 128 rows x 128 SNPs are in TMEM (and D was drained)
+                aphase ^= 1u;
             }
-            since_flush++;
-            expand_store(w0, 0);
-            // the next stage's first half travels while the second half is expanded
-            ring.next();
-            walk.advance();
-            if (it + 1 < len) {
-                tc_wait(bar(kBarFull + ring.stage), ring.parity);
-                load_words(smem_base + ring.stage * kStageBytes, 0, w0);
-            }
-            expand_store(w1, 1);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            asm volatile("bar.arrive %0, 160;" ::"r"(1 + t) : "memory");   // the sub-tile's 128 rows x 128 SNPs are in TMEM (and D was drained)
-            aphase ^= 1u;
         }
         drain();
-        store();
+        store(prev_tile);
     }
     tc_fence_before();
     __syncthreads();
