@@ -192,11 +192,8 @@ SIMU_B200_API int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, 
                                        double *pheno1, double *pheno2, int mode);
 
 /* find_freq + effect scaling + find_pheno (FAST mode) behind ONE call, everything on the device
- * (no host round trip between the passes).  GROUP4 panels only; rows 0..mc-1.  Default
- * implementation: the standard kernels back to back (SIMU_B200_OVERLAP_MB=<n> pipelines them in
- * chunks over two streams); SIMU_B200_FUSED_IMPL=onepass selects the experimental single
- * persistent kernel that counts a row block a few steps before it looks it up, so that HBM is read
- * once instead of twice (needs N < 2^19; parity-green but slower today).
+ * (no host round trip between the passes): the standard kernels queued back to back on the context's
+ * stream.  Compact panels (GROUP4 or SAMPLE16); rows 0..mc-1.
  * The call replaces this stretch of main():
  *     find_freq(...)                                   source.cc:1235
  *     draw / read effect sizes, scale them by het      source.cc:1238-1290
@@ -309,8 +306,8 @@ SIMU_B200_API int simu_b200_last_kernel_ms(simu_b200_ctx *ctx, int which, float 
 /* Per-kernel device timing for bench.py's roofline: when enabled, every launch of the hot
  * kernels is bracketed by a CUDA event pair on the launching stream (up to 512 pairs, then
  * recording stops).  kernel_id: 0 = allele counts, 1 = find_pheno EXACT, 2 = find_pheno FAST
- * main (LUT) kernel, 3 = LUT build, 4 = LUT slot reduce, 5 = sumsq/heritability, 6 = sort,
- * 7 = fused one-pass kernel.
+ * main kernel (tensor-core kernel on SAMPLE16 panels, lookup-table kernel otherwise), 3 = its table / weight
+ * build, 4 = its slot reduce, 5 = sumsq/heritability, 6 = sort.
  * profile_read synchronises the stream and returns the summed milliseconds and the number
  * of recorded launches; profile_enable resets the record. */
 SIMU_B200_API int simu_b200_profile_enable(simu_b200_ctx *ctx, int on);

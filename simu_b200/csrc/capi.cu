@@ -168,8 +168,6 @@ void simu_b200_close(simu_b200_ctx *ctx)
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-    for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -727,8 +725,8 @@ int simu_b200_find_freq_pheno_dev(simu_b200_ctx *ctx, int64_t mc, const double *
 {
     int rc = check_hot(ctx, "find_freq_pheno", mc, nullptr);
     if (rc) return rc;
-    if (ctx->layout != SIMU_B200_LAYOUT_GROUP4)
-        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: needs a GROUP4 panel (compact causal rows)");
+    if (ctx->layout == SIMU_B200_LAYOUT_ROWS)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: needs a compact panel (GROUP4 or SAMPLE16)");
     if (mc > ctx->panel_rows)
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: %lld causal rows but panel holds %lld", (long long)mc,
                         (long long)ctx->panel_rows);
@@ -741,21 +739,23 @@ int simu_b200_find_freq_pheno_dev(simu_b200_ctx *ctx, int64_t mc, const double *
         if (d_pheno2) CUDA_TRY(ctx, cudaMemsetAsync(d_pheno2, 0, (size_t)ctx->n_samples * 8, ctx->stream));
         return SIMU_B200_OK;
     }
-    // implementations: "overlap" (default) = the existing kernels as a chunked two-stream pipeline;
-    // "onepass" = the experimental single persistent kernel (HBM read once, slower today)
-    const char *impl = getenv("SIMU_B200_FUSED_IMPL");
-    if (!impl || strcmp(impl, "onepass") != 0)
-        return launch_pheno_overlap(ctx, mc, d_raw1, d_raw2, scale_op, d_component, d_s_pow, num_components, d_counts, d_freq,
-                                    d_effect1, d_effect2, d_pheno1, d_pheno2, (unsigned long long *)d_bad_index);
-    int fused = 1;
-    if (const char *e = getenv("SIMU_B200_FUSED_PREBUILT")) fused = atoi(e) ? 0 : 1;   // A/B: same schedule, two passes
-    if (!fused) {
-        if (scale_op != -1 || !d_freq)
-            return ctx_fail(ctx, SIMU_B200_EINVAL, "find_freq_pheno: the two-pass A/B mode needs scale_op -1 and a freq buffer");
-        if ((rc = launch_counts(ctx, nullptr, mc, d_counts, d_freq))) return rc;
-    }
-    return launch_pheno_fused(ctx, mc, d_raw1, d_raw2, scale_op, d_component, d_s_pow, num_components, d_counts, d_freq,
-                              d_effect1, d_effect2, d_pheno1, d_pheno2, (unsigned long long *)d_bad_index, fused, d_freq);
+    // counts -> effect scaling (the reference's host work between the passes, source.cc:1245-1262) -> FAST
+    // phenotypes, queued on one stream without a host round trip.  (A single-kernel version that read HBM once
+    // was built and measured in round 1: 2.4 ms against 1.06 ms for this sequence on config 2 -- the scaled
+    // effects of a SNP depend on its frequency over ALL samples -- and has been removed.)
+    if (!d_freq) d_freq = (double *)ctx_scratch(ctx, SCR_FREQ, (size_t)mc * 8);
+    if (!d_effect1) d_effect1 = (double *)ctx_scratch(ctx, SCR_X1, (size_t)mc * 8);
+    if (d_raw2 && !d_effect2) d_effect2 = (double *)ctx_scratch(ctx, SCR_X2, (size_t)mc * 8);
+    if (!d_freq || !d_effect1 || (d_raw2 && !d_effect2)) return SIMU_B200_ENOMEM;
+    if ((rc = launch_counts(ctx, nullptr, mc, d_counts, d_freq))) return rc;
+    if (d_effect1 != d_raw1) CUDA_TRY(ctx, cudaMemcpyAsync(d_effect1, d_raw1, (size_t)mc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_raw2 && d_effect2 != d_raw2)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_effect2, d_raw2, (size_t)mc * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (scale_op >= 0 && (rc = launch_scale_effects(ctx, d_freq, d_effect1, d_raw2 ? d_effect2 : nullptr, mc, d_component, d_s_pow,
+                                                    num_components, scale_op, (unsigned long long *)d_bad_index)))
+        return rc;
+    return simu_b200_find_pheno_dev(ctx, nullptr, mc, d_freq, d_effect1, d_raw2 ? d_effect2 : nullptr, d_pheno1, d_pheno2,
+                                    SIMU_B200_MODE_FAST);
 }
 
 int simu_b200_find_freq_pheno(simu_b200_ctx *ctx, int64_t mc, const double *raw1, const double *raw2, int scale_op,

@@ -1,5 +1,4 @@
-// GROUP4 allele counting, shared by counts_g4_kernel (counts.cu) and the counter warps of the
-// fused one-pass kernel (pheno_fused.cu).
+// GROUP4 allele counting (counts_g4_kernel, counts.cu).
 //
 // In a GROUP4 panel a 32-bit word holds 4 samples x 4 SNP rows (row r of the group in bits
 // 8s+2r, 8s+2r+1), so ONE pass over a group yields the counts of its four SNPs: the words go

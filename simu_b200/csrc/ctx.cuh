@@ -53,12 +53,9 @@ struct simu_b200_ctx {
 
     bool lut_attr_set[3] = {false, false, false};
     bool tc_attr_set = false;
-    bool fused_attr_set[3] = {false, false, false};
     int coop_sort_blocks = -1;           // co-resident blocks of the cooperative sort (-1: not queried)
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
-    std::vector<cudaEvent_t> chunk_events;   // overlap pipeline of find_freq_pheno
-    cudaStream_t aux_stream = nullptr;
     simu_b200_peer *peer = nullptr;          // multi-GPU exchange over NVLink peer memory (peer.cu)
     std::string err;
 };
@@ -79,7 +76,7 @@ void *ctx_scratch(simu_b200_ctx *ctx, int slot, size_t bytes);  // nullptr on fa
     } while (0)
 
 enum ProfId { PROF_COUNTS = 0, PROF_PHENO_EXACT = 1, PROF_LUT_MAIN = 2, PROF_LUT_BUILD = 3, PROF_LUT_REDUCE = 4,
-              PROF_REDUCTIONS = 5, PROF_SORT = 6, PROF_FUSED = 7 };
+              PROF_REDUCTIONS = 5, PROF_SORT = 6 };
 // record a begin / end event pair around a kernel when profiling is enabled
 int prof_begin(simu_b200_ctx *ctx, int id);      // returns slot or -1
 void prof_end(simu_b200_ctx *ctx, int slot);
@@ -108,20 +105,6 @@ int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, co
 // kernel (b), fast FP32 4-SNP LUT mode.  pheno_lut.cu
 int launch_pheno_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
                      const double *d_x1, const double *d_x2, double *d_y1, double *d_y2);
-
-// kernels (a)+(b) in one pass over HBM (GROUP4 panels, FAST mode).  pheno_lut.cu
-// op: -1 none, 0: x *= sqrt(pow(het, S)), 1: x /= sqrt(het); fused = 0 runs the same schedule on tables built
-// from d_freq_in (A/B runs).
-int launch_pheno_fused(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2, int op,
-                       const int32_t *d_comp, const double *d_spow, int ncomp, int32_t *d_counts, double *d_freq,
-                       double *d_x1, double *d_x2, double *d_y1, double *d_y2, unsigned long long *d_bad, int fused,
-                       const double *d_freq_in);
-
-// the same result from the existing kernels as a chunked two-stream pipeline (counts of chunk c+1 beside the
-// lookups of chunk c).  pheno_lut.cu
-int launch_pheno_overlap(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2, int op,
-                         const int32_t *d_comp, const double *d_spow, int ncomp, int32_t *d_counts, double *d_freq,
-                         double *d_x1, double *d_x2, double *d_y1, double *d_y2, unsigned long long *d_bad);
 
 // kernel (c): reductions.  reduce.cu
 int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out);

@@ -7,7 +7,9 @@
 //     apply_heritability         source.cc:1299  -> simu_b200_apply_heritability
 //     apply_liability_threshold  source.cc:1304  -> simu_b200_liability_order (+ host shuffles)
 // Causal selection, effect-size and noise draws stay on the host with the reference's RNG
-// order (rng.h).  Environment: SIMU_B200_MODE=exact|fast (default fast), SIMU_B200_DEVICE=n.
+// order (rng.h).  Environment: SIMU_B200_MODE=exact|fast (default exact: find_pheno bit-identical to the
+// reference on one GPU; fast = the tensor-core kernel, ~1e-12 of max|y|; anything else is an error),
+// SIMU_B200_DEVICE=n, SIMU_B200_DEVICES=all|0,1,...  The mode and the devices are written to <out>.log.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -459,6 +461,17 @@ void find_causals(const SimuOptions &o, Mt19937 &rng, Logger &log, const PlinkFi
         for (int i = 0; i < o.causal_n[c]; i++, p++) comp->at(perm[p]) = c;
 }
 
+// SIMU_B200_MODE: "exact" (the default: per-sample FP64 sums in ascending SNP order, bit-identical to
+// source.cc:986-996 on one GPU) or "fast" (tensor-core kernel, exact sum of 40-bit fixed-point weights, ~1e-12
+// of max|y|).  Anything else is an error -- a typo must not silently change the arithmetic.
+int find_pheno_mode()
+{
+    const char *m = getenv("SIMU_B200_MODE");
+    if (!m || !*m || std::string(m) == "exact") return SIMU_B200_MODE_EXACT;
+    if (std::string(m) == "fast") return SIMU_B200_MODE_FAST;
+    throw std::runtime_error(std::string("ERROR: SIMU_B200_MODE must be 'exact' or 'fast', got '") + m + "'");
+}
+
 // ---------------------------------------------------------------- the GPU session
 //
 // One context per GPU.  SIMU_B200_DEVICE=n (default 0) selects a single GPU; SIMU_B200_DEVICES=all or a
@@ -534,9 +547,9 @@ struct Gpu {
         }
         for_each_gpu([&](size_t d) {
             simu_b200_ctx *c = ctxs[d];
-            // compact causal panel (only the rows pio_next_row would read), sample-interleaved in groups of four
-            // rows so that find_pheno's FAST kernel reads its table index directly
-            check(c, simu_b200_panel_alloc_layout(c, std::max<size_t>(1, hi[d] - lo[d]), SIMU_B200_LAYOUT_GROUP4));
+            // compact causal panel (only the rows pio_next_row would read), sample-major in groups of sixteen rows:
+            // the layout of the tensor-core FAST kernel, of the ordered EXACT kernel and of the vertical counts
+            check(c, simu_b200_panel_alloc_layout(c, std::max<size_t>(1, hi[d] - lo[d]), SIMU_B200_LAYOUT_SAMPLE16));
             size_t pos = lo[d];
             int64_t dst = 0;
             for (size_t f = 0; f < pio.num_files() && pos < hi[d]; f++) {
@@ -581,8 +594,7 @@ void find_pheno(const SimuOptions &o, const std::vector<double> &freq_vec, const
     pheno1->assign(o.num_samples, 0.0);
     pheno2->clear();
     if (bivariate) pheno2->assign(o.num_samples, 0.0);
-    const char *m = getenv("SIMU_B200_MODE");
-    const int mode = (m && std::string(m) == "exact") ? SIMU_B200_MODE_EXACT : SIMU_B200_MODE_FAST;
+    const int mode = find_pheno_mode();
     const size_t D = gpu.ctxs.size();
     if (D == 1) {
         gpu.check(simu_b200_find_pheno(gpu.ctx, nullptr, (int64_t)mc, f.data(), x1.data(), bivariate ? x2.data() : nullptr,
@@ -751,9 +763,13 @@ int main(int argc, char *argv[])
             else find_causals_trait2_snp_offset(o, rng, &comp);
 
             timer.mark("causal_selection");
+            const int mode = find_pheno_mode();          // rejects a bad SIMU_B200_MODE before any work is done
             Gpu gpu;
             gpu.open(o.num_samples);
             timer.mark("cuda_context");
+            log << "simu_b200: find_pheno mode " << (mode == SIMU_B200_MODE_EXACT ? "exact" : "fast") << ", "
+                << gpu.ctxs.size() << " GPU" << (gpu.ctxs.size() == 1 ? "" : "s (phenotypes summed over SNP shards: tolerance-matched)")
+                << "\n";
 
             log << "Calculate allele frequencies (for causal markers only)... \n";
             std::vector<double> freq_vec;

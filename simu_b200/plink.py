@@ -158,8 +158,8 @@ class PlinkFiles:
         if v.size and np.any(np.diff(v) <= 0):
             raise ValueError("variant_indices must be strictly ascending")
         if ctx.panel_rows < max(1, v.size):
-            from . import capi                   # compact causal panel -> sample-interleaved groups of 4 rows
-            ctx.panel_alloc(max(1, v.size), capi.LAYOUT_GROUP4)
+            from . import capi                   # compact causal panel, sample-major in groups of 16 rows (the CLI's layout)
+            ctx.panel_alloc(max(1, v.size), capi.LAYOUT_SAMPLE16)
         dst = 0
         for f, local in self.split_by_file(v):
             ctx.panel_load_bed(self.files[f].bed_path, self.files[f].num_loci, local, dst_row=dst)
@@ -192,6 +192,39 @@ def deinterleave_group4(panel: np.ndarray, n_rows: int, n_samples: int) -> np.nd
     for r in range(n_rows):
         field = (panel[r // 4, :n_samples] >> (2 * (r % 4))) & 3
         np.bitwise_or.at(out[r], i // 4, (field << (2 * (i % 4))).astype(np.uint8))
+    return out
+
+
+# ------------------------------------------------------------- SAMPLE16 layout (host restatement)
+
+_BED_TO_DOSAGE = np.array([0, 3, 1, 2], np.uint32)     # .bed bit pairs 00, 01, 10, 11 -> dosage code (3 = missing)
+
+
+def interleave_sample16(packed_rows: np.ndarray, n_samples: int, group_words: int | None = None) -> np.ndarray:
+    """Packed .bed rows [M, >=ceil(N/4)] -> the SAMPLE16 panel image, uint32 [ceil(M/16), group_words]:
+    word i of group g = the genotypes of sample i for rows 16g..16g+15, row 16g in bits 0-1, re-coded as the
+    A2-allele dosage with 3 = missing (include/simu_b200.h, SIMU_B200_LAYOUT_SAMPLE16).  What
+    interleave16_kernel (csrc/stage.cu) produces on the device; rows beyond M and samples >= N read as 0."""
+    m = packed_rows.shape[0]
+    if group_words is None:
+        group_words = (n_samples + 127) // 128 * 128
+    i = np.arange(n_samples)
+    out = np.zeros(((m + 15) // 16, group_words), dtype=np.uint32)
+    for r in range(m):
+        field = (packed_rows[r, i // 4] >> (2 * (i % 4))) & 3
+        out[r // 16, :n_samples] |= _BED_TO_DOSAGE[field] << np.uint32(2 * (r % 16))
+    return out
+
+
+def deinterleave_sample16(panel: np.ndarray, n_rows: int, n_samples: int) -> np.ndarray:
+    """The inverse: SAMPLE16 panel image -> packed .bed rows [n_rows, ceil(N/4)] (padding bits 00)."""
+    B = row_bytes(n_samples)
+    i = np.arange(n_samples)
+    to_bed = np.array([0, 2, 3, 1], np.uint8)
+    out = np.zeros((n_rows, B), dtype=np.uint8)
+    for r in range(n_rows):
+        code = (panel[r // 16, :n_samples] >> np.uint32(2 * (r % 16))) & 3
+        np.bitwise_or.at(out[r], i // 4, (to_bed[code] << (2 * (i % 4))).astype(np.uint8))
     return out
 
 

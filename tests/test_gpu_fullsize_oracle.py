@@ -49,7 +49,7 @@ def _full(n, m, mc, k2, seed, gcta=False):
     """every causal row x every sample against the oracle"""
     causal = _causal(m, mc, seed)
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
         ctx.panel_synth_rows(PANEL_SEED, causal)
         rows = np.empty((mc, ctx.row_bytes), np.uint8)
         step = max(1, (256 << 20) // ctx.row_bytes)
@@ -84,7 +84,7 @@ def _column_block(n, m, mc, k2, seed, s0, ns=2048, count_rows=512):
     """ALL causal rows on the sample block [s0, s0 + ns) against the oracle"""
     causal = _causal(m, mc, seed)
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
         if mc == m:
             ctx.panel_synth(PANEL_SEED, 0, m)
         else:

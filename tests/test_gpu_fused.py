@@ -1,6 +1,5 @@
-"""simu_b200_find_freq_pheno (counts + effect scaling + FAST lookups behind one call, GROUP4 panels)
--- both implementations: "overlap" (default: the standard kernels as a chunked two-stream pipeline) and
-"onepass" (the experimental single persistent kernel) -- against the calls it replaces:
+"""simu_b200_find_freq_pheno (counts + effect scaling + FAST phenotypes behind one call, compact panels of
+both layouts) against the calls it replaces:
     find_freq -> scale_effects -> find_pheno
 counts and frequencies bit-exact, scaled effects within 1e-14, phenotypes within the FAST
 tolerance of the bit-exact EXACT mode (which the parity tests pin against the oracle)."""
@@ -15,11 +14,8 @@ CASES = [(4096, 64, False), (4096, 64, True), (5003, 257, True), (10000, 1000, F
          (20000, 3000, False), (1, 5, False), (7, 1, True), (250001, 130, False), (500000, 80, False), (40000, 5000, True)]
 
 
-@pytest.fixture(params=["overlap", "overlap-1MB-chunks", "onepass"])
-def impl(request, monkeypatch):
-    monkeypatch.setenv("SIMU_B200_FUSED_IMPL", "onepass" if request.param == "onepass" else "overlap")
-    if request.param == "overlap-1MB-chunks":
-        monkeypatch.setenv("SIMU_B200_OVERLAP_MB", "1")       # many chunks even on the small cases
+@pytest.fixture(params=[capi.LAYOUT_GROUP4, capi.LAYOUT_SAMPLE16], ids=["group4", "sample16"])
+def impl(request):
     return request.param
 
 
@@ -31,7 +27,7 @@ def test_one_call_matches_the_three_calls(n, mc, k2, impl):
     comp = rng.integers(0, 2, mc).astype(np.int32)
     sp1, sp2 = np.array([-1.0, 0.5]), np.array([-0.25, -1.0])
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        ctx.panel_alloc(mc, impl)
         ctx.panel_synth(99, 0, mc)
         counts, freq = ctx.find_freq()
         for op in ((-1, 0, 1) if n > 100 else (-1,)):          # tiny N: monomorphic variants -> zero het
@@ -46,10 +42,10 @@ def test_one_call_matches_the_three_calls(n, mc, k2, impl):
                 assert np.max(np.abs(y2 - e2)) <= 1e-5 * np.max(np.abs(e2))
 
 
-def test_one_call_reports_zero_het_and_needs_group4(impl):
+def test_one_call_reports_zero_het_and_needs_a_compact_panel(impl):
     n, mc = 3000, 40
     with capi.Context(n) as ctx:
-        ctx.panel_alloc(mc, capi.LAYOUT_GROUP4)
+        ctx.panel_alloc(mc, impl)
         rows = np.zeros((mc, (n + 3) // 4), np.uint8)           # all hom A1 -> freq 1 -> het 0
         rows[5:] = ctx_rows = np.random.default_rng(0).integers(0, 256, (mc - 5, (n + 3) // 4), dtype=np.uint8)
         ctx.panel_put_rows(0, rows)

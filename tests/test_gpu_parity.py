@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
 PANEL_SEED = 20240901
 FAST_RTOL = 1e-5
 # every test that does not address rows through a row list runs on both panel layouts
-LAYOUTS = pytest.mark.parametrize("layout", [capi.LAYOUT_ROWS, capi.LAYOUT_GROUP4], ids=["rows", "group4"])
+LAYOUTS = pytest.mark.parametrize("layout", [capi.LAYOUT_ROWS, capi.LAYOUT_GROUP4, capi.LAYOUT_SAMPLE16],
+                                  ids=["rows", "group4", "sample16"])
 
 
 def _effects(mc, seed, k2=True):
@@ -248,6 +249,40 @@ def test_group4_byte_is_the_table_index():
         want = codes[4 * g] | (codes[4 * g + 1] << 2) | (codes[4 * g + 2] << 4) | (codes[4 * g + 3] << 6)
         assert np.array_equal(raw[g, :n], want.astype(np.uint8))
     assert np.array_equal(raw, host_image)
+
+
+def test_sample16_append_at_any_offset_image_and_row_lists():
+    """SAMPLE16 (the CLI's layout): rows appended in pieces that do not end on 16-row group boundaries give the
+    same panel as one put; the device image equals the host restatement of the layout (dosage codes, word per
+    sample, zero padding); get_rows undoes layout and coding; row lists are refused."""
+    import torch
+    n, m = 1001, 37
+    rows = _panel(n, m)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(m, capi.LAYOUT_SAMPLE16)
+        assert ctx.layout == capi.LAYOUT_SAMPLE16 and ctx.group_stride == 4 * 1024
+        for lo, hi in ((0, 5), (5, 6), (6, 19), (19, 37)):
+            ctx.panel_put_rows(lo, rows[lo:hi])
+        assert np.array_equal(ctx.panel_get_rows(0, m), rows)
+        assert np.array_equal(ctx.panel_get_rows(13, 9), rows[13:22])
+        ctx.sync()
+        gw = ctx.group_stride // 4
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (3, gw), "typestr": "<u4", "data": (ctx.panel_ptr, False), "version": 2,
+                                        "strides": None}
+        raw = torch.as_tensor(_Mem(), device="cuda").cpu().numpy().view(np.uint32)
+        assert np.array_equal(raw, plink.interleave_sample16(rows, n))
+        counts, freq = ctx.find_freq()
+        ctx.panel_put_rows(17, rows[0:2])                     # overwrite two rows inside a group: the neighbours keep their bits
+        back = ctx.panel_get_rows(0, m)
+        with pytest.raises(capi.SimuB200Error) as ei:
+            ctx.find_freq(rows=np.array([1, 2], np.int32))
+        assert ei.value.status == capi.EINVAL and "SAMPLE16" in str(ei.value)
+    oc, of = oracle.find_freq(rows, n)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+    expect = rows.copy(); expect[17:19] = rows[0:2]
+    assert np.array_equal(back, expect)
 
 
 def test_group4_rejects_row_lists():

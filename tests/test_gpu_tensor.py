@@ -1,0 +1,92 @@
+"""The tensor-core find_pheno kernel (SAMPLE16 panels, MODE_FAST; csrc/pheno_tc.cu) against the oracle
+(src/source.cc:951-1006).  The kernel computes the EXACT integer sum of per-SNP weights quantised to 40-bit
+fixed point relative to the largest weight of the trait, so its error is set by that quantisation alone:
+the tests state 1e-9 of max|y| where the effect sizes are well scaled (the tolerance north_star asks for is
+1e-5) and check the 2^-41 max|W| per-term bound where they are not."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from simu_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(rows, n, x1, x2, freq=None):
+    mc = rows.shape[0]
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+        ctx.panel_put_rows(0, rows)
+        counts, f = ctx.find_freq()
+        y = ctx.find_pheno(f if freq is None else freq, x1, x2, mode=capi.MODE_FAST)
+    return counts, f, y
+
+
+# shapes around every granularity of the kernel: 128-sample sub-tiles, 768-sample tiles, 16-row groups,
+# 128-SNP stages, the 16384-SNP drain interval, more steps than SMs, fewer steps than SMs
+@pytest.mark.parametrize("n,mc,k2", [(1, 1, True), (127, 15, False), (129, 17, True), (767, 127, True), (768, 128, False),
+                                     (769, 129, True), (1537, 2049, False), (5003, 16384, True), (777, 16400, False),
+                                     (2000, 40000, True), (33333, 257, True), (100003, 300, False)])
+def test_tensor_kernel_matches_oracle(n, mc, k2):
+    rows = oracle.synth_rows(20240901, 11, mc, n)
+    rng = np.random.default_rng(n * 7 + mc)
+    x1 = rng.standard_normal(mc)
+    x2 = 0.5 * x1 + np.sqrt(0.75) * rng.standard_normal(mc) if k2 else None
+    counts, freq, (y1, y2) = _run(rows, n, x1, x2)
+    oc, of = oracle.find_freq_threaded(rows, n, 8)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+    o1, o2 = oracle.find_pheno(rows, n, of, x1, x2, threads=8)
+    assert np.max(np.abs(y1 - o1)) <= 1e-9 * max(np.max(np.abs(o1)), 1e-300)
+    if k2:
+        assert np.max(np.abs(y2 - o2)) <= 1e-9 * max(np.max(np.abs(o2)), 1e-300)
+
+
+def test_tensor_kernel_heavy_missingness_and_all_missing_rows():
+    n, mc = 3001, 400
+    rng = np.random.default_rng(5)
+    rows = oracle.synth_rows(3, 0, mc, n)
+    codes = np.stack([oracle.unpack(rows[j], n) for j in range(mc)])
+    codes[rng.random((mc, n)) < 0.3] = 3
+    codes[7] = 3                                                   # a row with every genotype missing: freq 0 (source.cc:875)
+    codes[100] = 0                                                 # monomorphic
+    rows = np.stack([oracle.pack(codes[j]) for j in range(mc)])
+    x1, x2 = rng.standard_normal(mc), rng.standard_normal(mc)
+    counts, freq, (y1, y2) = _run(rows, n, x1, x2)
+    oc, of = oracle.find_freq(rows, n)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of) and freq[7] == 0.0 and counts[7, 3] == n
+    o1, o2 = oracle.find_pheno(rows, n, of, x1, x2)
+    assert np.max(np.abs(y1 - o1)) <= 1e-9 * np.max(np.abs(o1))
+    assert np.max(np.abs(y2 - o2)) <= 1e-9 * np.max(np.abs(o2))
+
+
+def test_tensor_kernel_quantisation_bound_with_badly_scaled_effects():
+    """One effect 1e9 times the others: the small ones are represented to 2^-41 of the LARGE one, which is the
+    documented bound (error per term <= 2^-41 max|W| * 3); trait 2 has its own scale and stays tight."""
+    n, mc = 2048, 1000
+    rows = oracle.synth_rows(9, 0, mc, n)
+    rng = np.random.default_rng(1)
+    x1 = rng.standard_normal(mc)
+    x1[500] = 1e9
+    x2 = rng.standard_normal(mc)
+    _, freq, (y1, y2) = _run(rows, n, x1, x2)
+    o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2)
+    wmax = 1e9 * 3.0                                               # |x (1 + 2f)| <= 3 |x|
+    assert np.max(np.abs(y1 - o1)) <= mc * 3 * wmax * 2.0 ** -41 + 1e-9 * np.max(np.abs(o1))
+    assert np.max(np.abs(y2 - o2)) <= 1e-9 * np.max(np.abs(o2))
+
+
+def test_tensor_kernel_zero_effects_and_is_deterministic():
+    n, mc = 5000, 3000
+    rows = oracle.synth_rows(2, 0, mc, n)
+    rng = np.random.default_rng(2)
+    x1 = rng.standard_normal(mc)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+        ctx.panel_put_rows(0, rows)
+        _, freq = ctx.find_freq()
+        z1, z2 = ctx.find_pheno(freq, np.zeros(mc), np.zeros(mc), mode=capi.MODE_FAST)
+        assert not z1.any() and not z2.any()
+        a1, a2 = ctx.find_pheno(freq, x1, -x1, mode=capi.MODE_FAST)
+        b1, b2 = ctx.find_pheno(freq, x1, -x1, mode=capi.MODE_FAST)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)      # integer sums + fixed slot order: same bits every run
+    assert np.array_equal(a2, -a1)                                 # sign symmetry of the fixed-point weights
