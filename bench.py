@@ -60,15 +60,6 @@ def _peaks():
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def _traffic(workload, kernel, layout="rows"):
-    """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/), or None."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        return t[workload if layout == "rows" else f"{workload}:{layout}"][kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
-
-
 def _causal_rows(w, rank):
     rng = np.random.default_rng(1 + rank)            # --seed 1 (+rank: each GPU owns its own slice)
     if w["mc"] == w["m"]:
@@ -101,49 +92,60 @@ def alg_bytes(w):
 # ------------------------------------------------------------------ clocks
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU, sampled IN-PROCESS through NVML every 5 ms by a thread
+    (an `nvidia-smi -lms` child process needs ~100 ms for its first row, longer than a short timed region)."""
 
-    def __init__(self, gpu_index: int):
-        self.samples, self.proc, self.t = [], None, None
+    _BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
+    def __init__(self, gpu_index: int, period: float = 0.005):
+        self.samples, self.period, self._stop, self.t = [], period, threading.Event(), None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._one()                                   # at least one sample exists before any timed region starts
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:                            # no NVML: the line says so instead of inventing clocks
+            self.nv, self.err = None, repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
+    def _one(self):
+        nv = self.nv
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            power = None
+        self.samples.append((time.time(), float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), int(reasons), power))
+
+    def _run(self):
+        while not self._stop.wait(self.period):
+            try:
+                self._one()
+            except Exception:
+                break
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
 
     def summary(self, t0, t1):
-        rows = [s for s in self.samples if t0 <= s[0] <= t1 + 0.15] or self.samples[-5:]
-        sm, mx, reasons = [], [], set()
-        for _, line in rows:
-            f = [x.strip() for x in line.split(",")]
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": getattr(self, "err", "no NVML")}
+        rows = [s for s in self.samples if t0 <= s[0] <= t1]
+        inside = len(rows)
+        if not rows:                                      # region shorter than the period: the nearest samples around it
+            rows = sorted(self.samples, key=lambda s: abs(s[0] - 0.5 * (t0 + t1)))[:3]
+        reasons = sorted(name for name, bit in self._BAD.items() if any(r[2] & bit for r in rows))
+        power = [r[3] for r in rows if r[3] is not None]
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(rows), "samples_inside_timed_region": inside,
+                "power_w_max": max(power) if power else None, "source": "NVML in-process, 5 ms period"}
 
 
 # ------------------------------------------------------------ reference arm
@@ -239,6 +241,221 @@ class _DevMem:
                                          "version": 2, "strides": None}
 
 
+def _roofline(kernel, alg_bytes_per_launch, ms, n_launches, peaks, peak_src, traffic):
+    if not n_launches:
+        return None
+    ach = alg_bytes_per_launch / (ms / n_launches * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+            "traffic_captured_at": (traffic or {}).get("commit"), "peak_source": peak_src,
+            "ms_per_launch": ms / n_launches, "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launches_timed": n_launches}
+
+
+KERNEL_NAMES = {  # layout -> (counts kernel, FAST kernel, EXACT kernel)
+    "s16": ("counts_s16_kernel", "pheno_tc_kernel", "pheno_exact_s16_kernel"),
+    "group4": ("counts_g4_kernel", "pheno_lut_g4_kernel", "pheno_exact_g4_kernel"),
+    "rows": ("counts_kernel", "pheno_lut_kernel", "pheno_exact_kernel"),
+}
+
+
+class Workload:
+    """One BASELINE config resident on this rank's GPU: panel, vectors and the step function."""
+
+    def __init__(self, args, name, rank, world, local, dev, stream):
+        import torch
+        import torch.distributed as dist
+        from simu_b200 import capi
+        self.torch, self.dist, self.capi = torch, dist, capi
+        self.args, self.name, self.rank, self.world, self.dev, self.stream = args, name, rank, world, dev, stream
+        w = self.w = WORKLOADS[name]
+        n, m, mc, k = w["n"], w["m"], w["mc"], w["k"]
+        self.ctx = ctx = capi.Context(n, device=local)
+        ctx.set_stream(stream.cuda_stream)
+        self.causal = causal = _causal_rows(w, rank)
+        self.compact = args.layout in ("group4", "s16")
+        self.layout_id = {"s16": capi.LAYOUT_SAMPLE16, "group4": capi.LAYOUT_GROUP4, "rows": capi.LAYOUT_ROWS}[args.layout]
+        if self.compact:
+            # what the drop-in CLI keeps in HBM: the causal rows only (the reference reads no others,
+            # source.cc:852-863), compact and in causal order
+            ctx.panel_alloc(mc, self.layout_id)
+            if mc == m:
+                ctx.panel_synth(PANEL_SEED, rank * m, m)
+            else:
+                ctx.panel_synth_rows(PANEL_SEED, causal.astype(np.int64) + rank * m)
+            self.d_rows = None
+        else:
+            # the whole slice of the .bed resident, row-major; causal rows gathered through a row list
+            ctx.panel_alloc(m)
+            ctx.panel_synth(PANEL_SEED, rank * m, m)        # each GPU holds its own slice of the panel
+            self.d_rows = torch.from_numpy(causal).to(dev) if mc != m else None
+        self.rows_ptr = self.d_rows.data_ptr() if self.d_rows is not None else 0
+        self.d_counts = torch.empty((mc, 4), dtype=torch.int32, device=dev)
+        self.d_freq = torch.empty(mc, dtype=torch.float64, device=dev)
+        ctx.find_freq_dev(self.rows_ptr, mc, self.d_counts.data_ptr(), self.d_freq.data_ptr())
+        torch.cuda.synchronize()
+        self.gcta = name == "config2"                       # --gcta-sigma: effects scaled by het^-1/2 between the passes
+        r1, r2 = _raw_effects(w, rank)
+        self.x1, self.x2 = _effects(w, self.d_freq.cpu().numpy(), rank) if self.gcta else (r1, r2)
+        self.d_r1 = torch.from_numpy(r1).to(dev)
+        self.d_r2 = torch.from_numpy(r2).to(dev) if k == 2 else None
+        self.d_x1 = torch.from_numpy(self.x1).to(dev)
+        self.d_x2 = torch.from_numpy(self.x2).to(dev) if k == 2 else None
+        self.d_spow = torch.tensor([-1.0, -1.0], dtype=torch.float64, device=dev)
+        self.d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.d_y = torch.zeros((k, n), dtype=torch.float64, device=dev)   # [trait][sample], contiguous for one all-reduce
+        g = torch.Generator(device="cpu").manual_seed(5)
+        self.d_noise = torch.randn((k, n), dtype=torch.float64, generator=g).to(dev)   # e: same draws on every rank
+        self.d_misc = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.d_index = torch.empty(n, dtype=torch.int32, device=dev)
+        self.d_is_case = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.max_ncon = n - int(np.floor(np.float32(0.1) * np.float32(n)))        # --k 0.1 (source.cc:1038-1039)
+        self.mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
+        # the one exchange step: all-reduce over NVLink peer memory (simu_b200_peer_*), NCCL only if peer access is unavailable
+        self.allreduce = "nccl"
+        if world > 1 and args.allreduce in ("auto", "peer"):
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, ctx.peer_init(rank, world, k * n))
+                ctx.peer_connect(handles)
+                ok = torch.ones(1, device=dev)
+            except capi.SimuB200Error as e:
+                print(f"rank {rank}: peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            self.allreduce = "peer" if ok.item() > 0 else "nccl"
+        # the scaling runs inside the step when the device-resident one-call form applies
+        self.one_call = self.gcta and self.compact and self.mode == capi.MODE_FAST
+
+    def step(self):
+        ctx, w, k, n, mc = self.ctx, self.w, self.w["k"], self.w["n"], self.w["mc"]
+        d_y = self.d_y
+        if self.one_call:      # find_freq -> effect scaling (--gcta-sigma) -> find_pheno, no host round trip
+            ctx.find_freq_pheno_dev(mc, self.d_r1.data_ptr(), self.d_r2.data_ptr() if k == 2 else 0, 0, 0, self.d_spow.data_ptr(), 1,
+                                    self.d_counts.data_ptr(), self.d_freq.data_ptr(), self.d_x1.data_ptr(),
+                                    self.d_x2.data_ptr() if k == 2 else 0, d_y[0].data_ptr(),
+                                    d_y[1].data_ptr() if k == 2 else 0, self.d_bad.data_ptr())
+        else:
+            ctx.find_freq_dev(self.rows_ptr, mc, self.d_counts.data_ptr(), self.d_freq.data_ptr())
+            ctx.find_pheno_dev(self.rows_ptr, mc, self.d_freq.data_ptr(), self.d_x1.data_ptr(),
+                               self.d_x2.data_ptr() if k == 2 else 0, d_y[0].data_ptr(), d_y[1].data_ptr() if k == 2 else 0, self.mode)
+        if self.world > 1:                                # the path's one exchange step (SURVEY.md 8e)
+            if self.allreduce == "peer":
+                ctx.peer_allreduce_dev(d_y.data_ptr(), k * n)
+            else:
+                self.dist.all_reduce(d_y)
+        for t in range(k):
+            ctx.sumsq_dev(d_y[t].data_ptr(), n, self.d_misc[t].data_ptr())
+            ctx.heritability_dev(HSQ[t], d_y[t].data_ptr(), n, self.d_noise[t].data_ptr(), self.d_misc[t].data_ptr(),
+                                 self.d_misc[4 + 2 * t].data_ptr())
+        if w["cc"]:      # default --ncas/--ncon: both pools fully labelled -> the order statistic decides
+            if self.args.cc_sort:
+                ctx.liability_order_dev(d_y[0].data_ptr(), n, self.d_index.data_ptr())
+            else:
+                ctx.liability_split_dev(d_y[0].data_ptr(), n, self.max_ncon, self.d_is_case.data_ptr())
+
+    def measure(self, steps, warmup, sampler, prof_steps=20):
+        """-> dict: value, ms_per_step, kernel_ms, rooflines, clocks, launches.  The timed region replays ONE
+        CUDA graph of the step per iteration when the step could be captured (single GPU; the launch-bound
+        sparse configs are 10 launches of microseconds each); per-kernel times for the roofline come from a
+        second, eager region with the library's event pairs around every launch."""
+        torch, dist, ctx, w = self.torch, self.dist, self.ctx, self.w
+        n, mc, k = w["n"], w["mc"], w["k"]
+        for _ in range(warmup):
+            self.step()
+        torch.cuda.synchronize()
+        if steps <= 0:      # as many steps as fill ~60 ms, so that the 5 ms clock sampler sees the timed region
+            t0 = time.perf_counter()
+            self.step()
+            torch.cuda.synchronize()
+            steps = int(min(5000, max(10, 0.06 / max(time.perf_counter() - t0, 1e-6))))
+            if self.world > 1:
+                t = torch.tensor([steps], dtype=torch.int64, device=self.dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                steps = int(t.item())
+        graph = None
+        if self.world == 1 and self.args.graph != "off":
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self.step()
+                g.replay()
+                torch.cuda.synchronize()
+                graph = g
+            except Exception as e:
+                print(f"{self.name}: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+                torch.cuda.synchronize()
+                ctx.set_stream(self.stream.cuda_stream)
+                self.step()
+                torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
+        e0.record(self.stream)
+        if graph is not None:
+            for _ in range(steps):
+                graph.replay()
+        else:
+            for _ in range(steps):
+                self.step()
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+        ms_total = e0.elapsed_time(e1)
+        # kernels per step: counted over one eager step (a graph replay launches the same kernels)
+        l0 = ctx.launches
+        ctx.profile_enable(True)
+        for _ in range(prof_steps):
+            self.step()
+        torch.cuda.synchronize()
+        launches_per_step = (ctx.launches - l0) // prof_steps
+        prof = {name: ctx.profile_read(i) for name, i in (("counts", 0), ("pheno_exact", 1), ("pheno_fast", 2),
+                                                         ("pheno_fast_build", 3), ("pheno_fast_reduce", 4), ("cc_order", 6))}
+        ctx.profile_enable(False)
+        if self.world > 1:
+            t = torch.tensor([ms_total], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        ms_step = ms_total / steps
+        _, bytes_counts, bytes_pheno = alg_bytes(w)
+        peaks, peak_src = _peaks()
+        names = KERNEL_NAMES[self.args.layout]
+        fast = self.mode == self.capi.MODE_FAST
+        main_ms, main_n = prof["pheno_fast" if fast else "pheno_exact"]
+        cnt_ms, cnt_n = prof["counts"]
+        out = {
+            "value": n * mc * k * self.world / (ms_step * 1e-3), "ms_per_step": ms_step, "steps": steps,
+            "cuda_graph": graph is not None, "gpu_launches_per_step": int(launches_per_step),
+            "bed_gbs": 2 * mc * ((n + 3) // 4) * self.world / (ms_step * 1e-3) / 1e9,
+            "roofline": _roofline(names[1] if fast else names[2], bytes_pheno, main_ms, main_n, peaks, peak_src,
+                                  _traffic(self.name, names[1] if fast else names[2], self.args.layout)),
+            "roofline_counts": _roofline(names[0], bytes_counts, cnt_ms, cnt_n, peaks, peak_src,
+                                         _traffic(self.name, names[0], self.args.layout)),
+            "kernel_ms": {kname: (v[0] / v[1] if v[1] else None) for kname, v in prof.items()},
+            "clocks": sampler.summary(t_wall0, t_wall1) if sampler else None,
+            "checksum_device": float(self.d_y.abs().sum().item()),
+        }
+        return out
+
+    def close(self):
+        self.ctx.close()
+
+
+def _traffic(workload, kernel, layout):
+    """DRAM bytes per launch from a committed `ncu --set full` capture (profiles/ncu_traffic.json; each entry
+    names the commit it was captured at), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t[f"{workload}:{layout}"][kernel]
+    except Exception:
+        return None
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -255,140 +472,31 @@ def run_ours(args, w):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local) if rank == 0 else None          # started before any panel is generated
+    stream = torch.cuda.Stream(device=dev)           # one stream for torch ops, NCCL hand-off and our kernels
+    torch.cuda.set_stream(stream)
     n, m, mc, k = w["n"], w["m"], w["mc"], w["k"]
     B, bytes_counts, bytes_pheno = alg_bytes(w)
 
-    ctx = capi.Context(n, device=local)
-    stream = torch.cuda.Stream(device=dev)           # one stream for torch ops, NCCL hand-off and our kernels
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    causal = _causal_rows(w, rank)
-    g4 = args.layout in ("group4", "s16")           # compact causal panel
-    compact_layout = capi.LAYOUT_SAMPLE16 if args.layout == "s16" else capi.LAYOUT_GROUP4
-    if g4:
-        # what the drop-in CLI keeps in HBM: the causal rows only (the reference reads no others,
-        # source.cc:852-863), compact and in causal order, four rows sample-interleaved per group
-        ctx.panel_alloc(mc, compact_layout)
-        if mc == m:
-            ctx.panel_synth(PANEL_SEED, rank * m, m)
-        else:
-            ctx.panel_synth_rows(PANEL_SEED, causal.astype(np.int64) + rank * m)
-        d_rows = None
-    else:
-        # the whole slice of the .bed resident, row-major; causal rows gathered through a row list
-        ctx.panel_alloc(m)
-        ctx.panel_synth(PANEL_SEED, rank * m, m)        # each GPU holds its own slice of the panel
-        d_rows = torch.from_numpy(causal).to(dev) if mc != m else None
-    rows_ptr = d_rows.data_ptr() if d_rows is not None else 0
-    d_counts = torch.empty((mc, 4), dtype=torch.int32, device=dev)
-    d_freq = torch.empty(mc, dtype=torch.float64, device=dev)
-    ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
-    torch.cuda.synchronize()
-    x1, x2 = _effects(w, d_freq.cpu().numpy(), rank)
-    d_x1 = torch.from_numpy(x1).to(dev)
-    d_x2 = torch.from_numpy(x2).to(dev) if k == 2 else None
-    d_y = torch.zeros((k, n), dtype=torch.float64, device=dev)       # [trait][sample], contiguous for one all-reduce
-    g = torch.Generator(device="cpu").manual_seed(5)
-    d_noise = torch.randn((k, n), dtype=torch.float64, generator=g).to(dev)   # e: same draws on every rank
-    d_misc = torch.zeros(8, dtype=torch.float64, device=dev)
-    d_index = torch.empty(n, dtype=torch.int32, device=dev)
-    d_is_case = torch.empty(n, dtype=torch.uint8, device=dev)
-    max_ncon = n - int(np.floor(np.float32(0.1) * np.float32(n)))        # --k 0.1 (source.cc:1038-1039)
-    mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
-    # the one exchange step: one-shot all-reduce over NVLink peer memory (simu_b200_peer_*), NCCL as the fallback
-    allreduce = "nccl"
-    # "auto": the one-shot form reads (world-1) x the payload per rank -- it wins while that stays below ~6 MB
-    # (8 GPUs: 24 vs 29 us at 0.8 MB, 35 vs 30 us at 1.6 MB, 118 vs 68 us at 8 MB; 2 GPUs: always)
-    want_peer = args.allreduce == "peer" or (args.allreduce == "auto" and (world - 1) * k * n * 8 <= 6 << 20)
-    if world > 1 and want_peer:
-        try:
-            handles = [None] * world
-            dist.all_gather_object(handles, ctx.peer_init(rank, world, k * n))
-            ctx.peer_connect(handles)
-            ok = torch.ones(1, device=dev)
-        except capi.SimuB200Error as e:
-            print(f"rank {rank}: peer all-reduce unavailable ({e}); using NCCL", file=sys.stderr)
-            ok = torch.zeros(1, device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        allreduce = "peer" if ok.item() > 0 else "nccl"
-    fused = args.fused and g4 and mode == capi.MODE_FAST
-    if fused:      # one pass: the raw draws go in, the kernel scales them by het^-1/2 (--gcta-sigma) itself
-        r1, r2 = _raw_effects(w, rank)
-        fused_op = 0
-        if os.environ.get("SIMU_B200_FUSED_PREBUILT"):      # A/B: same schedule, tables prebuilt from a counts pass
-            r1, r2, fused_op = x1, x2, -1
-        d_r1 = torch.from_numpy(r1).to(dev)
-        d_r2 = torch.from_numpy(r2).to(dev) if k == 2 else None
-        d_spow = torch.tensor([-1.0, -1.0], dtype=torch.float64, device=dev)
-        d_bad = torch.zeros(1, dtype=torch.int64, device=dev)
-
-    def step():
-        if fused:
-            ctx.find_freq_pheno_dev(mc, d_r1.data_ptr(), d_r2.data_ptr() if k == 2 else 0, fused_op, 0, d_spow.data_ptr(), 1,
-                                    d_counts.data_ptr(), d_freq.data_ptr(), d_x1.data_ptr(),
-                                    d_x2.data_ptr() if k == 2 else 0, d_y[0].data_ptr(),
-                                    d_y[1].data_ptr() if k == 2 else 0, d_bad.data_ptr())
-        else:
-            ctx.find_freq_dev(rows_ptr, mc, d_counts.data_ptr(), d_freq.data_ptr())
-            ctx.find_pheno_dev(rows_ptr, mc, d_freq.data_ptr(), d_x1.data_ptr(), d_x2.data_ptr() if k == 2 else 0,
-                               d_y[0].data_ptr(), d_y[1].data_ptr() if k == 2 else 0, mode)
-        if world > 1:                                # the path's one exchange step
-            if allreduce == "peer":
-                ctx.peer_allreduce_dev(d_y.data_ptr(), k * n)
-            else:
-                dist.all_reduce(d_y)
-        for t in range(k):
-            ctx.sumsq_dev(d_y[t].data_ptr(), n, d_misc[t].data_ptr())
-            ctx.heritability_dev(HSQ[t], d_y[t].data_ptr(), n, d_noise[t].data_ptr(), d_misc[t].data_ptr(),
-                                 d_misc[4 + 2 * t].data_ptr())
-        if w["cc"]:      # default --ncas/--ncon: both pools fully labelled -> the order statistic decides
-            if args.cc_sort:
-                ctx.liability_order_dev(d_y[0].data_ptr(), n, d_index.data_ptr())
-            else:
-                ctx.liability_split_dev(d_y[0].data_ptr(), n, max_ncon, d_is_case.data_ptr())
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ctx.profile_enable(True)
-    launches0 = ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    ms_total = e0.elapsed_time(e1)
-    launches = ctx.launches - launches0
-    prof = {name: ctx.profile_read(i) for name, i in (("counts", 0), ("pheno_exact", 1), ("lut_main", 2),
-                                                     ("lut_build", 3), ("lut_reduce", 4), ("cc_order", 6), ("fused", 7))}
-    ctx.profile_enable(False)
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    wl = Workload(args, args.workload, rank, world, local, dev, stream)
+    ctx, mode, causal = wl.ctx, wl.mode, wl.causal
+    res = wl.measure(args.steps, args.warmup, sampler)
+    ms_step, value = res["ms_per_step"], res["value"]
     updates_step = n * mc * k * world
-    value = updates_step / (ms_step * 1e-3)
-    clocks = sampler.summary(t_wall0, t_wall1) if sampler else None
-    y_check = float(d_y.abs().sum().item())
+    x1, x2 = wl.x1, wl.x2
+    # the e2e leg must see the effects the timed step used (scaled on the device inside the step for --gcta-sigma)
+    if wl.one_call:
+        x1 = wl.d_x1.cpu().numpy()
+        x2 = wl.d_x2.cpu().numpy() if k == 2 else None
+    y_check = res["checksum_device"]
 
     if args.no_e2e:
         if rank == 0:
-            emit({"profiling_run": True, "ms_per_step": ms_step, "value": value,
-                  "kernel_ms": {kn: (v[0] / v[1] if v[1] else None) for kn, v in prof.items()}})
+            emit({"profiling_run": True, "ms_per_step": ms_step, "value": value, "kernel_ms": res["kernel_ms"],
+                  "cuda_graph": res["cuda_graph"]})
         if sampler:
             sampler.stop()
-        ctx.close()
+        wl.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -396,7 +504,7 @@ def run_ours(args, w):
     # ------------------------------------------------ e2e through the host-buffer C ABI
     e2e_steps = max(2, min(args.steps, 5))
     host_rows = torch.empty((mc, B), dtype=torch.uint8, pin_memory=True)     # the causal rows as packed .bed rows
-    if g4:
+    if wl.compact:
         ctx.panel_get_rows_ptr(0, mc, host_rows.data_ptr(), B)
     else:
         panel_view = torch.as_tensor(_DevMem(ctx.panel_ptr, (m, ctx.row_stride)), device=dev)
@@ -407,9 +515,10 @@ def run_ours(args, w):
             host_rows[lo:hi].copy_(panel_view.index_select(0, idx)[:, :B])
         torch.cuda.synchronize()
         del panel_view
+    noise_h = wl.d_noise.cpu().numpy()
+    wl.close()                                       # the e2e context stages its own panel
     ctx2 = capi.Context(n, device=local)
-    ctx2.panel_alloc(mc, compact_layout if g4 else capi.LAYOUT_ROWS)
-    noise_h = d_noise.cpu().numpy()
+    ctx2.panel_alloc(mc, wl.layout_id if wl.compact else capi.LAYOUT_ROWS)
     e2e_y = None
 
     def e2e_step():
@@ -453,6 +562,8 @@ def run_ours(args, w):
            "api": "simu_b200_panel_put_rows + find_freq + find_pheno + apply_heritability (host buffers)"}
     # the device-resident and host-buffer paths must agree (same inputs, same kernels)
     e2e_check = float(np.abs(e2e_y[0]).sum() + (np.abs(e2e_y[1]).sum() if k == 2 else 0.0))
+    parity_ok = abs(e2e_check - y_check) <= 1e-9 * abs(y_check)
+    ctx2.close()
 
     # ------------------------------------------------ CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -465,53 +576,57 @@ def run_ours(args, w):
         cpu = {"value": n * s * k / dt, "unit": "updates/s", "cores": 1, "kind": kind,
                "sample": f"first {s} of {mc} causal SNP rows x {n} samples, one pass ({dt:.1f} s)",
                "host_cores": os.cpu_count()}
+    del host_rows
+
+    # ------------------------------------------------ the other BASELINE configs, same arm, fewer steps
+    also = {}
+    if not args.no_also:
+        for name in ("config4", "config5", "config3", "config1"):
+            if name == args.workload:
+                continue
+            torch.cuda.empty_cache()
+            o = Workload(args, name, rank, world, local, dev, stream)
+            r = o.measure(args.also_steps, 3, sampler, prof_steps=5)
+            ow = WORKLOADS[name]
+            also[name] = {"desc": ow["desc"], "n_samples": ow["n"], "n_causal_per_gpu": ow["mc"], "traits": ow["k"],
+                          "parallelism": f"snp-shard x{world}, 1 all-reduce ({o.allreduce})" if world > 1 else "single GPU",
+                          **{kk: r[kk] for kk in ("value", "ms_per_step", "steps", "cuda_graph", "gpu_launches_per_step", "bed_gbs",
+                                                  "roofline", "roofline_counts", "kernel_ms", "clocks")}}
+            o.close()
 
     if rank == 0:
-        peaks, peak_src = _peaks()
-        main_key = "lut_main" if mode == capi.MODE_FAST else "pheno_exact"
-        main_ms, main_n = prof[main_key]
-        cnt_ms, cnt_n = prof["counts"]
-        roof = None
-        if main_n:
-            ach = bytes_pheno / (main_ms / main_n * 1e-3) / 1e9
-            sfx = "_g4_kernel" if g4 else "_kernel"
-            roof = {"bound": "hbm", "kernel": ("pheno_lut" if mode == capi.MODE_FAST else "pheno_exact") + sfx,
-                    "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": _traffic(args.workload, "pheno_lut_kernel" if mode == capi.MODE_FAST else "pheno_exact_kernel", args.layout),
-                    "peak_source": peak_src, "ms_per_launch": main_ms / main_n,
-                    "algorithmic_bytes_per_launch": bytes_pheno, "launches_timed": main_n}
-        counts_roof = None
-        if cnt_n:
-            ach = bytes_counts / (cnt_ms / cnt_n * 1e-3) / 1e9
-            counts_roof = {"kernel": "counts_g4_kernel" if g4 else "counts_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": ach / peaks["hbm_gbs"], "traffic": _traffic(args.workload, "counts_kernel", args.layout),
-                           "ms_per_launch": cnt_ms / cnt_n,
-                           "algorithmic_bytes_per_launch": bytes_counts}
+        compact = wl.compact
+        panel_desc = {"s16": "causal rows only, compact, SAMPLE16 (16 rows sample-major, dosage-coded)",
+                      "group4": "causal rows only, compact, GROUP4 (4 rows sample-interleaved)",
+                      "rows": "whole .bed slice row-major + causal row list"}[args.layout]
         line = {
             "metric": "genotype_effect_updates_per_s", "value": value, "unit": "updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32-table/f64-accumulate" if mode == capi.MODE_FAST else "f64",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("s32-tensor-core/f64-recombine" if args.layout == "s16" else "f32-table/f64-accumulate") if mode == capi.MODE_FAST else "f64",
             "data": "synthetic",
             "config": {"workload": args.workload, "desc": w["desc"], "n_samples": n, "panel_rows_per_gpu": m,
-                       "hbm_panel_rows_per_gpu": mc if g4 else m,
-                       "n_causal_per_gpu": mc, "traits": k, "mode": args.mode,
-                       "hbm_panel": ("causal rows only, compact, GROUP4 (4 rows sample-interleaved)" if g4 else
-                                     "whole .bed slice row-major + causal row list"),
+                       "hbm_panel_rows_per_gpu": mc if compact else m,
+                       "n_causal_per_gpu": mc, "traits": k, "mode": args.mode, "hbm_panel": panel_desc,
+                       "step": "find_freq -> effect scaling on the device -> find_pheno -> apply_heritability per trait" if wl.one_call
+                               else "find_freq -> find_pheno -> apply_heritability per trait" + (" -> liability split" if w["cc"] else ""),
+                       "cuda_graph": res["cuda_graph"],
                        "l2": f"inputs larger than L2 ({mc * B / 1e6:.0f} MB of causal rows per pass, 126 MB L2)",
-                       "parallelism": f"snp-shard x{world}, 1 all-reduce ({allreduce})" if world > 1 else "single GPU"},
-            "bed_gbs": 2 * mc * B * world / (ms_step * 1e-3) / 1e9,
-            "roofline": roof, "roofline_counts": counts_roof, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks,
-            "kernel_ms": {kname: (v[0] / v[1] if v[1] else None) for kname, v in prof.items()},
-            "checksum": {"device": y_check, "e2e": e2e_check},
+                       "parallelism": f"snp-shard x{world}, 1 all-reduce ({wl.allreduce})" if world > 1 else "single GPU"},
+            "bed_gbs": res["bed_gbs"],
+            "roofline": res["roofline"], "roofline_counts": res["roofline_counts"], "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(res["gpu_launches_per_step"] * args.steps), "clocks": res["clocks"],
+            "kernel_ms": res["kernel_ms"],
+            "checksum": {"device": y_check, "e2e": e2e_check}, "parity_check": bool(parity_ok),
+            "also": also,
         }
         emit(line)
     if sampler:
         sampler.stop()
-    ctx2.close()
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if not parity_ok:
+        raise SystemExit(f"bench.py: device-resident and host-buffer results differ: {y_check!r} vs {e2e_check!r}")
 
 
 _REAL_STDOUT = None
@@ -544,12 +659,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--layout", default="group4", choices=["group4", "rows", "s16"],
-                    help="HBM panel: compact causal rows in GROUP4 layout (what the CLI stages) or the whole "
-                         ".bed slice row-major with a causal row list")
-    ap.add_argument("--fused", action="store_true",
-                    help="one call: simu_b200_find_freq_pheno (counts + effect scaling + lookups on the device; "
-                         "SIMU_B200_FUSED_IMPL=onepass selects the experimental single-kernel version)")
+    ap.add_argument("--layout", default="s16", choices=["s16", "group4", "rows"],
+                    help="HBM panel: compact causal rows in SAMPLE16 layout (what the CLI stages; tensor-core FAST kernel), "
+                         "in GROUP4 layout (lookup-table FAST kernel), or the whole .bed slice row-major with a causal row list")
+    ap.add_argument("--graph", default="auto", choices=["auto", "off"],
+                    help="single GPU: replay one CUDA graph of the step per timed iteration (auto) or launch eagerly (off)")
+    ap.add_argument("--no-also", action="store_true", help="skip the `also` block (the other BASELINE configs)")
+    ap.add_argument("--also-steps", type=int, default=0, help="steps per `also` workload (0: as many as fill ~60 ms)")
     ap.add_argument("--cc-sort", action="store_true",
                     help="--cc workloads: full liability argsort (needed when --ncas/--ncon select a subset) instead of the split")
     ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"],

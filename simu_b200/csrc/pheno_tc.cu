@@ -226,43 +226,106 @@ tc_prepare_kernel(const double *__restrict__ freq, const double *__restrict__ x1
     }
 }
 
-// pass 2: the weight tiles.  One thread writes the 16 K-bytes of one (64-SNP block, group q, plane, column n).
+// pass 2: the weight tiles.  One work item (blk, t), t < 8 * K, converts the 16 SNPs of one (64-SNP block, group q,
+// plane, trait) to fixed point ONCE and writes all eight digit columns of that trait (128 bytes).
 template <int K>
-__global__ void __launch_bounds__(128)
-tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
-                  const TcScale *__restrict__ scale, uint8_t *__restrict__ wt)
+__device__ __forceinline__ void weight_item(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
+                                            int64_t mc, const double (&inv_quantum)[2], uint8_t *__restrict__ wt, int64_t blk, int t)
 {
-    const int64_t blk = blockIdx.x;
-    const int t = threadIdx.x;
-    const int q = t >> 5, plane = (t >> 4) & 1, n = t & 15;
-    const int k = n >> 3, d = n & 7;
-    uint32_t out[4] = {0, 0, 0, 0};
-    if (k < K && d < kDigits) {
-        const int e = scale[k].exponent;
+    const int q = t & 3, plane = (t >> 2) & 1, k = t >> 3;
+    uint32_t out[8][4];
 #pragma unroll
-        for (int kk = 0; kk < 16; kk++) {
-            const int s = kk >> 2, b = kk & 3;                         // byte b of the word masked for field s
-            const int64_t j = blk * kStepSnps + 16 * q + 4 * b + s;   // SNP 4b + s of the group
-            if (j < mc) {
-                double wp, wm, c;
-                weights_of(freq[j], k == 0 ? x1[j] : x2[j], wp, wm, c);
-                long long v = __double2ll_rn(ldexp(plane ? wm : wp, -e));   // |v| <= 2^40
-                v <<= 6 - 2 * s;                                        // the A byte carries the factor 4^s
-                long long digit = 0;
+    for (int d = 0; d < 8; d++)
 #pragma unroll
-                for (int i = 0; i < kDigits; i++) {
-                    if (i <= d) {
-                        digit = (long long)(signed char)(v & 0xFF);
-                        v = (v - digit) >> 8;
-                    }
-                }
-                out[kk >> 2] |= (uint32_t)(uint8_t)digit << (8 * (kk & 3));
+        for (int i = 0; i < 4; i++) out[d][i] = 0;
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+        const int s = kk >> 2, b = kk & 3;                         // byte b of the word masked for field s
+        const int64_t j = blk * kStepSnps + 16 * q + 4 * b + s;   // SNP 4b + s of the group
+        if (j < mc) {
+            double wp, wm, c;
+            weights_of(freq[j], k == 0 ? x1[j] : x2[j], wp, wm, c);
+            long long v = __double2ll_rn((plane ? wm : wp) * inv_quantum[k]);   // |v| <= 2^40 (the quantum is a power of two)
+            v <<= 6 - 2 * s;                                        // the A byte carries the factor 4^s
+#pragma unroll
+            for (int d = 0; d < kDigits; d++) {
+                const long long digit = (long long)(signed char)(v & 0xFF);
+                v = (v - digit) >> 8;
+                out[d][kk >> 2] |= (uint32_t)(uint8_t)digit << (8 * (kk & 3));
             }
         }
     }
-    // sub-tile q at q*512; element (n, kappa): (kappa / 16) * 256 + (n / 8) * 128 + (n % 8) * 16 + kappa % 16
-    uint4 *dst = reinterpret_cast<uint4 *>(wt + blk * kWTileBytes + q * 512 + plane * 256 + (n >> 3) * 128 + (n & 7) * 16);
-    *dst = make_uint4(out[0], out[1], out[2], out[3]);
+    // sub-tile q at q*512; element (n, kappa): (kappa / 16) * 256 + (n / 8) * 128 + (n % 8) * 16 + kappa % 16, n = 8 k + d
+    uint4 *dst = reinterpret_cast<uint4 *>(wt + blk * kWTileBytes + q * 512 + plane * 256 + k * 128);
+#pragma unroll
+    for (int d = 0; d < 8; d++) dst[d] = make_uint4(out[d][0], out[d][1], out[d][2], out[d][3]);
+    if (K == 1) {                                                   // the second trait's columns are zero
+#pragma unroll
+        for (int d = 0; d < 8; d++) dst[8 + d] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+constexpr int kWeightItems = 16;        // per 64-SNP block: 4 groups x 2 planes x 2 traits (K = 1: the first 8)
+template <int K>
+__global__ void __launch_bounds__(128)
+tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
+                  int64_t ntiles, const TcScale *__restrict__ scale, uint8_t *__restrict__ wt)
+{
+    const double inv_quantum[2] = {ldexp(1.0, -scale[0].exponent), K == 2 ? ldexp(1.0, -scale[1].exponent) : 0.0};
+    const int64_t item = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (item < ntiles * (8 * K)) weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)));
+}
+
+// both passes in ONE CTA for small causal sets (the sparse configs are launch-bound: two dependent launches and a
+// grid-wide ticket cost more than the arithmetic).  Same summation order as nothing else: the constant is a sum
+// over a fixed strided partition followed by a fixed tree, so it is deterministic for a given mc.
+constexpr int kSmallThreads = 1024, kSmallMc = 4096;
+template <int K>
+__global__ void __launch_bounds__(kSmallThreads)
+tc_small_prepare_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
+                        int64_t ntiles, TcScale *__restrict__ scale, uint8_t *__restrict__ wt)
+{
+    __shared__ double ssum[K][kSmallThreads], smax[K][kSmallThreads];
+    __shared__ int sexp[2];
+    double sum[K], mx[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { sum[k] = 0.0; mx[k] = 0.0; }
+    for (int64_t j = threadIdx.x; j < mc; j += kSmallThreads) {
+        const double f = freq[j];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double wp, wm, c;
+            weights_of(f, k == 0 ? x1[j] : x2[j], wp, wm, c);
+            sum[k] += c;
+            mx[k] = fmax(mx[k], fmax(fabs(wp), fabs(wm)));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) { ssum[k][threadIdx.x] = sum[k]; smax[k][threadIdx.x] = mx[k]; }
+    __syncthreads();
+    for (int s = kSmallThreads / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                ssum[k][threadIdx.x] += ssum[k][threadIdx.x + s];
+                smax[k][threadIdx.x] = fmax(smax[k][threadIdx.x], smax[k][threadIdx.x + s]);
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < K) {
+        const int k = threadIdx.x;
+        const double m = smax[k][0];
+        const int e = (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 - kFracBits : 0;
+        scale[k].constant = ssum[k][0];
+        scale[k].exponent = e;
+        scale[k].pad = 0;
+        sexp[k] = e;
+    }
+    __syncthreads();
+    const double inv_quantum[2] = {ldexp(1.0, -sexp[0]), K == 2 ? ldexp(1.0, -sexp[1]) : 0.0};
+    for (int64_t item = threadIdx.x; item < ntiles * (8 * K); item += kSmallThreads)
+        weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)));
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -390,15 +453,16 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         // operands -> uniform registers), one elected lane issues.  The hand-over from the expanders is a named
         // barrier of 160 threads on which the 128 expander threads only ARRIVE: they never wait for the issue.
         const int t = warp - kMmaWarp0;
-        const uint32_t d_tmem = tmem + kColD + 16 * t;
-        const uint32_t a_tmem = tmem + kColA + 64 * t;
-        const uint32_t bar_aempty = bar(kBarAEmpty + t), bar_dfull = bar(kBarDFull + t);
+        const uint32_t d_tmem = pin(tmem + kColD + 16 * t);
+        const uint32_t a_tmem = pin(tmem + kColA + 64 * t);
+        const uint32_t bar_aempty = pin(bar(kBarAEmpty + t)), bar_dfull = pin(bar(kBarDFull + t)), bar_id = pin(1 + t);
+        const uint32_t wt0 = pin(smem_base + 2 * kBoxBytes);
         Ring ring;
         while (walk.next(seg)) {
             for (int i = 0; i < seg.n; i++, ring.next()) {
                 tc_wait(bar(kBarFull + ring.stage), ring.parity);       // the stage's weight tiles have landed
-                const uint32_t desc = wtile_desc_lo(smem_base + ring.stage * kStageBytes + 2 * kBoxBytes);
-                asm volatile("bar.sync %0, 160;" ::"r"(1 + t) : "memory");     // A buffer written, D drained
+                const uint32_t desc = wtile_desc_lo(wt0 + ring.stage * kStageBytes);
+                asm volatile("bar.sync %0, 160;" ::"r"(bar_id) : "memory");    // A buffer written, D drained
                 tc_fence_after();
 #pragma unroll
                 for (int q = 0; q < kStageGroups; q++)      // the first MMA of a segment overwrites D
@@ -413,9 +477,10 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
         const int t = warp >> 2;                                // sub-tile
         const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;         // this warp's quarter of the TMEM lanes
         const int my = t * 128 + (warp & 3) * 32 + lane;        // sample within the tile
-        const uint32_t d_tmem = tmem + kColD + 16 * t + lane_field;
-        const uint32_t a_tmem = tmem + kColA + 64 * t + lane_field;   // the sub-tile's A buffer: 64 columns = one stage
-        const uint32_t bar_aempty = bar(kBarAEmpty + t), bar_dfull = bar(kBarDFull + t);
+        const uint32_t d_tmem = pin(tmem + kColD + 16 * t + lane_field);
+        const uint32_t a_tmem = pin(tmem + kColA + 64 * t + lane_field);   // the sub-tile's A buffer: 64 columns = one stage
+        const uint32_t bar_aempty = pin(bar(kBarAEmpty + t)), bar_dfull = pin(bar(kBarDFull + t)), bar_id = pin(1 + t);
+        const uint32_t bar_full0 = pin(bar(kBarFull)), bar_empty0 = pin(bar(kBarEmpty));
         // this thread's word in a stage: box (384 samples) x group row (1536 B) x sample
         const uint32_t my_off = pin(smem_base + (uint32_t)((my / kBoxSamples) * kBoxBytes + (my % kBoxSamples) * 4));
         double y[K];
@@ -489,18 +554,18 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
             for (int i = 0; i < seg.n; i++) {
                 load_words(ring.stage, 1, w1);                  // the stage's words are then all in registers
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarEmpty + ring.stage));
+                if (lane == 0) mbar_arrive(bar_empty0 + 8 * ring.stage);
                 expand_store(w0, 0);
                 // the next stage's first half travels while the second half is expanded
                 ring.next();
                 if (--remaining > 0) {
-                    tc_wait(bar(kBarFull + ring.stage), ring.parity);
+                    tc_wait(bar_full0 + 8 * ring.stage, ring.parity);
                     load_words(ring.stage, 0, w0);
                 }
                 expand_store(w1, 1);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                asm volatile("bar.arrive %0, 160;" ::"r"(1 + t) : "memory");   // 128 rows x 128 SNPs are in TMEM (and D was drained)
+                asm volatile("bar.arrive %0, 160;" ::"r"(bar_id) : "memory");  // 128 rows x 128 SNPs are in TMEM (and D was drained)
                 aphase ^= 1u;
             }
         }
@@ -586,10 +651,16 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     int rc = make_panel_map(ctx, &map);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
     int ps = prof_begin(ctx, PROF_LUT_BUILD);
-    tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);
-    tc_weights_kernel<K><<<(unsigned)(nblocks * kHalves), 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, scale, wt);
+    if (mc <= kSmallMc) {
+        tc_small_prepare_kernel<K><<<1, kSmallThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt);
+    } else {
+        CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
+        tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);
+        const int64_t items = nblocks * kHalves * 8 * K;
+        tc_weights_kernel<K><<<(unsigned)((items + 127) / 128), 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt);
+        ctx->launches++;
+    }
     prof_end(ctx, ps);
 
     TcParams p;
@@ -601,7 +672,7 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     ps = prof_begin(ctx, PROF_LUT_REDUCE);
     tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2);
     prof_end(ctx, ps);
-    ctx->launches += 4;
+    ctx->launches += 3;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_tc launch");
 }
 

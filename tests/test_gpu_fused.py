@@ -36,10 +36,11 @@ def test_one_call_matches_the_three_calls(n, mc, k2, impl):
             c, f, g1, g2, y1, y2 = ctx.find_freq_pheno(r1, r2, op, comp, sp1, sp2)
             assert np.array_equal(c, counts) and np.array_equal(f, freq)
             assert np.allclose(g1, x1, rtol=1e-14, atol=0)
-            assert np.max(np.abs(y1 - e1)) <= 1e-5 * max(np.max(np.abs(e1)), 1e-300)
+            # + the fixed-point floor of the tensor-core kernel (2^-41 max|W| per term), which shows when y cancels to ~0
+            assert np.max(np.abs(y1 - e1)) <= 1e-5 * np.max(np.abs(e1)) + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x1))
             if k2:
                 assert np.allclose(g2, x2, rtol=1e-14, atol=0)
-                assert np.max(np.abs(y2 - e2)) <= 1e-5 * np.max(np.abs(e2))
+                assert np.max(np.abs(y2 - e2)) <= 1e-5 * np.max(np.abs(e2)) + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x2))
 
 
 def test_one_call_reports_zero_het_and_needs_a_compact_panel(impl):

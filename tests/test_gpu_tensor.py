@@ -36,9 +36,11 @@ def test_tensor_kernel_matches_oracle(n, mc, k2):
     oc, of = oracle.find_freq_threaded(rows, n, 8)
     assert np.array_equal(counts, oc) and np.array_equal(freq, of)
     o1, o2 = oracle.find_pheno(rows, n, of, x1, x2, threads=8)
-    assert np.max(np.abs(y1 - o1)) <= 1e-9 * max(np.max(np.abs(o1)), 1e-300)
+    # 1e-9 of max|y|, plus the fixed-point floor (each term carries <= 2^-41 max|W| * 3 with |W| <= 3 |x|), which
+    # only shows where y cancels to nothing: one sample's centred genotypes are all zero
+    assert np.max(np.abs(y1 - o1)) <= 1e-9 * np.max(np.abs(o1)) + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x1))
     if k2:
-        assert np.max(np.abs(y2 - o2)) <= 1e-9 * max(np.max(np.abs(o2)), 1e-300)
+        assert np.max(np.abs(y2 - o2)) <= 1e-9 * np.max(np.abs(o2)) + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x2))
 
 
 def test_tensor_kernel_heavy_missingness_and_all_missing_rows():
