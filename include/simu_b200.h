@@ -191,6 +191,20 @@ SIMU_B200_API int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, 
                                        const double *freq, const double *effect1, const double *effect2,
                                        double *pheno1, double *pheno2, int mode);
 
+/* find_pheno over the rows of the CURRENT panel, ADDED to the sums pheno1/pheno2 already hold: for causal sets
+ * larger than HBM the host loads them panel by panel, in ascending order (the reference streams the same rows
+ * from disk, source.cc:968-984), and calls this once per panel after zeroing pheno.  EXACT mode continues every
+ * sample's chain of FP64 additions, so the result is bit-identical to a single pass (and to the reference);
+ * FAST mode adds each panel's exact fixed-point sum.  SAMPLE16 panels only; rows 0..mc-1. */
+SIMU_B200_API int simu_b200_find_pheno_accumulate(simu_b200_ctx *ctx, int64_t mc, const double *freq,
+                                                  const double *effect1, const double *effect2, double *pheno1,
+                                                  double *pheno2, int mode);
+
+/* Free and total HBM of the context's device, in bytes; `free` counts the current panel as free (a new
+ * panel_alloc replaces it).  panel_bytes: what panel_alloc_layout(num_rows, layout) allocates. */
+SIMU_B200_API int simu_b200_mem_info(simu_b200_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes);
+SIMU_B200_API int64_t simu_b200_panel_bytes(const simu_b200_ctx *ctx, int64_t num_rows, int layout);
+
 /* find_freq + effect scaling + find_pheno (FAST mode) behind ONE call, everything on the device
  * (no host round trip between the passes): the standard kernels queued back to back on the context's
  * stream.  Compact panels (GROUP4 or SAMPLE16); rows 0..mc-1.

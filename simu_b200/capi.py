@@ -47,6 +47,9 @@ SIGNATURES = {
     "simu_b200_panel_get_rows": (_i32, [_vp, _i64, _i64, _vp, _i64]),
     "simu_b200_find_freq": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "simu_b200_find_pheno": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "simu_b200_find_pheno_accumulate": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "simu_b200_mem_info": (_i32, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "simu_b200_panel_bytes": (_i64, [_vp, _i64, _i32]),
     "simu_b200_find_freq_pheno": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp,
                                          C.POINTER(C.c_int64)]),
     "simu_b200_find_freq_pheno_dev": (_i32, [_vp, _i64, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -241,6 +244,25 @@ class Context:
         self._check(self.lib.simu_b200_find_pheno(self.h, _np_ptr(r), mc, _np_ptr(f), _np_ptr(x1), _np_ptr(x2),
                                                   _np_ptr(y1), _np_ptr(y2), mode))
         return y1, y2
+
+    def find_pheno_accumulate(self, freq, effect1, effect2, pheno1, pheno2=None, mode: int = MODE_EXACT):
+        """pheno += the contributions of the current (SAMPLE16) panel's rows, in place; see include/simu_b200.h."""
+        f = np.ascontiguousarray(freq, dtype=np.float64)
+        x1 = np.ascontiguousarray(effect1, dtype=np.float64)
+        x2 = None if effect2 is None else np.ascontiguousarray(effect2, dtype=np.float64)
+        if pheno1.dtype != np.float64 or not pheno1.flags.c_contiguous or (pheno2 is not None and pheno2.dtype != np.float64):
+            raise ValueError("pheno arrays must be contiguous float64 (they are updated in place)")
+        self._check(self.lib.simu_b200_find_pheno_accumulate(self.h, f.size, _np_ptr(f), _np_ptr(x1), _np_ptr(x2),
+                                                             _np_ptr(pheno1), _np_ptr(pheno2), mode))
+
+    def mem_info(self):
+        """-> (free_bytes, total_bytes) of the device; the current panel counts as free."""
+        f, t = C.c_int64(), C.c_int64()
+        self._check(self.lib.simu_b200_mem_info(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
+    def panel_bytes(self, rows: int, layout: int) -> int:
+        return int(self.lib.simu_b200_panel_bytes(self.h, rows, layout))
 
     def find_freq_pheno(self, raw1, raw2=None, scale_op: int = -1, component=None, s_pow1=None, s_pow2=None, mc=None):
         """find_freq + effect scaling + find_pheno (FAST) in one pass (GROUP4 panels).

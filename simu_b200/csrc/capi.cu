@@ -232,6 +232,7 @@ int simu_b200_panel_free(simu_b200_ctx *ctx)
     if (ctx->panel) { CUDA_TRY(ctx, cudaFree(ctx->panel)); }
     ctx->panel = nullptr;
     ctx->panel_rows = 0;
+    ctx->panel_bytes = 0;
     return SIMU_B200_OK;
 }
 
@@ -251,6 +252,7 @@ int simu_b200_panel_alloc_layout(simu_b200_ctx *ctx, int64_t num_rows, int layou
         return ctx_fail(ctx, SIMU_B200_ENOMEM, "panel_alloc: cannot allocate %zu bytes of HBM (%s)", bytes,
                         cudaGetErrorString(e));
     ctx->panel_rows = num_rows;
+    ctx->panel_bytes = bytes;
     ctx->layout = layout;
     // pitch padding is never interpreted by the kernels (they mask to N); zero it once so that
     // panel_get_rows and debuggers see defined bytes.  GROUP4: rows of a group that have not been
@@ -585,9 +587,9 @@ int simu_b200_find_freq_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t m
     return launch_counts(ctx, d_rows, mc, d_counts, d_freq);
 }
 
-int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
-                             const double *d_effect1, const double *d_effect2, double *d_pheno1,
-                             double *d_pheno2, int mode)
+static int find_pheno_dev_impl(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                               const double *d_effect1, const double *d_effect2, double *d_pheno1,
+                               double *d_pheno2, int mode, int accumulate)
 {
     int rc = check_hot(ctx, "find_pheno", mc, d_rows);
     if (rc) return rc;
@@ -597,14 +599,46 @@ int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t 
     if (!d_freq || !d_effect1 || !d_pheno1 || ((d_effect2 == nullptr) != (d_pheno2 == nullptr)))
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: NULL argument (effect2/pheno2 must be both set or both NULL)");
     if (ctx->layout == SIMU_B200_LAYOUT_SAMPLE16) {
-        if (mode == SIMU_B200_MODE_EXACT) return launch_pheno_exact_s16(ctx, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
-        if (mode == SIMU_B200_MODE_FAST) return launch_pheno_tc(ctx, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
+        if (mode == SIMU_B200_MODE_EXACT) {
+            if (accumulate && mc == 0) return SIMU_B200_OK;
+            return launch_pheno_exact_s16(ctx, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2, accumulate);
+        }
+        if (mode == SIMU_B200_MODE_FAST) return launch_pheno_tc(ctx, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2, accumulate);
     }
+    if (accumulate)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno_accumulate: needs a SAMPLE16 panel");
     if (mode == SIMU_B200_MODE_EXACT)
         return launch_pheno_exact(ctx, d_rows, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
     if (mode == SIMU_B200_MODE_FAST)
         return launch_pheno_lut(ctx, d_rows, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2);
     return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: unknown mode %d", mode);
+}
+
+int simu_b200_find_pheno_dev(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,
+                             const double *d_effect1, const double *d_effect2, double *d_pheno1,
+                             double *d_pheno2, int mode)
+{
+    return find_pheno_dev_impl(ctx, d_rows, mc, d_freq, d_effect1, d_effect2, d_pheno1, d_pheno2, mode, 0);
+}
+
+int simu_b200_mem_info(simu_b200_ctx *ctx, int64_t *free_bytes, int64_t *total_bytes)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t f = 0, t = 0;
+    CUDA_TRY(ctx, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f + (ctx->panel ? (int64_t)ctx->panel_bytes : 0);    // the current panel would be replaced
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return SIMU_B200_OK;
+}
+
+int64_t simu_b200_panel_bytes(const simu_b200_ctx *ctx, int64_t num_rows, int layout)
+{
+    if (!ctx || num_rows < 0) return -1;
+    if (layout == SIMU_B200_LAYOUT_SAMPLE16) return (num_rows + 15) / 16 * ctx->s16_stride;
+    if (layout == SIMU_B200_LAYOUT_GROUP4) return (num_rows + 3) / 4 * ctx->group_stride;
+    if (layout == SIMU_B200_LAYOUT_ROWS) return num_rows * ctx->row_stride;
+    return -1;
 }
 
 int simu_b200_sumsq_dev(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out)
@@ -684,8 +718,9 @@ int simu_b200_find_freq(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, int
     return SIMU_B200_OK;
 }
 
-int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, const double *freq,
-                         const double *effect1, const double *effect2, double *pheno1, double *pheno2, int mode)
+static int find_pheno_host_impl(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, const double *freq,
+                                const double *effect1, const double *effect2, double *pheno1, double *pheno2, int mode,
+                                int accumulate)
 {
     int rc = check_hot(ctx, "find_pheno", mc, rows);
     if (rc || (rc = check_row_list(ctx, "find_pheno", rows, mc))) return rc;
@@ -693,9 +728,11 @@ int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, co
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: NULL argument (effect2/pheno2 must be both set or both NULL)");
     if (mode != SIMU_B200_MODE_EXACT && mode != SIMU_B200_MODE_FAST)
         return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno: unknown mode %d", mode);
+    if (accumulate && ctx->layout != SIMU_B200_LAYOUT_SAMPLE16)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "find_pheno_accumulate: needs a SAMPLE16 panel");
     const int64_t n = ctx->n_samples;
     if (mc == 0) {                                           // source.cc:962-966: phenotypes start at 0
-        for (int64_t i = 0; i < n; i++) { pheno1[i] = 0; if (pheno2) pheno2[i] = 0; }
+        if (!accumulate) for (int64_t i = 0; i < n; i++) { pheno1[i] = 0; if (pheno2) pheno2[i] = 0; }
         return SIMU_B200_OK;
     }
     void *d_rows = nullptr, *d_freq = nullptr, *d_x1 = nullptr, *d_x2 = nullptr;
@@ -706,9 +743,13 @@ int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, co
     double *d_y1 = (double *)ctx_scratch(ctx, SCR_Y1, (size_t)n * 8);
     double *d_y2 = effect2 ? (double *)ctx_scratch(ctx, SCR_Y2, (size_t)n * 8) : nullptr;
     if (!d_y1 || (effect2 && !d_y2)) return SIMU_B200_ENOMEM;
+    if (accumulate) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_y1, pheno1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (pheno2) CUDA_TRY(ctx, cudaMemcpyAsync(d_y2, pheno2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
-    rc = simu_b200_find_pheno_dev(ctx, (const int32_t *)d_rows, mc, (const double *)d_freq, (const double *)d_x1,
-                                  (const double *)d_x2, d_y1, d_y2, mode);
+    rc = find_pheno_dev_impl(ctx, (const int32_t *)d_rows, mc, (const double *)d_freq, (const double *)d_x1,
+                             (const double *)d_x2, d_y1, d_y2, mode, accumulate);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(pheno1, d_y1, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -716,6 +757,18 @@ int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, co
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->last_ms[1], ctx->ev_a, ctx->ev_b));
     return SIMU_B200_OK;
+}
+
+int simu_b200_find_pheno(simu_b200_ctx *ctx, const int32_t *rows, int64_t mc, const double *freq,
+                         const double *effect1, const double *effect2, double *pheno1, double *pheno2, int mode)
+{
+    return find_pheno_host_impl(ctx, rows, mc, freq, effect1, effect2, pheno1, pheno2, mode, 0);
+}
+
+int simu_b200_find_pheno_accumulate(simu_b200_ctx *ctx, int64_t mc, const double *freq, const double *effect1,
+                                    const double *effect2, double *pheno1, double *pheno2, int mode)
+{
+    return find_pheno_host_impl(ctx, nullptr, mc, freq, effect1, effect2, pheno1, pheno2, mode, 1);
 }
 
 int simu_b200_find_freq_pheno_dev(simu_b200_ctx *ctx, int64_t mc, const double *d_raw1, const double *d_raw2,

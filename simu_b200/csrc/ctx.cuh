@@ -24,6 +24,7 @@ struct simu_b200_ctx {
     int64_t row_stride = 0;   // pitch in HBM
     uint8_t *panel = nullptr;
     int64_t panel_rows = 0;
+    size_t panel_bytes = 0;
     int layout = SIMU_B200_LAYOUT_ROWS;   // how the panel is laid out in HBM (simu_b200_layout)
     int64_t group_stride = 0; // GROUP4: bytes per 4-row group = round_up(N, 128), one byte per sample
     int64_t s16_stride = 0;   // SAMPLE16: bytes per 16-row group = 4 * round_up(N, 128), one word per sample
@@ -93,10 +94,11 @@ int launch_counts_g4_range(simu_b200_ctx *ctx, cudaStream_t stream, int64_t firs
 int launch_counts_s16(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int32_t *d_counts, double *d_freq);
 
 // kernel (b) on SAMPLE16 panels: tcgen05 integer MMA (FAST) and ordered FP64 (EXACT).  pheno_tc.cu, pheno_exact.cu
+// accumulate != 0: d_y holds the sums over earlier panels' rows and this panel's rows are added to them
 int launch_pheno_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
-                    double *d_y1, double *d_y2);
+                    double *d_y1, double *d_y2, int accumulate);
 int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
-                           double *d_y1, double *d_y2);
+                           double *d_y1, double *d_y2, int accumulate);
 
 // kernel (b), exact FP64 ordered mode.  pheno_exact.cu
 int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,

@@ -188,16 +188,18 @@ template <int K>
 __global__ void __launch_bounds__(kThreads)
 pheno_exact_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int64_t mc, int64_t n_samples,
                        const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
-                       double *__restrict__ y1, double *__restrict__ y2)
+                       double *__restrict__ y1, double *__restrict__ y2, int accumulate)
 {
     __shared__ __align__(16) double tbl[kChunk][4][K];      // [snp][dosage code][trait]
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n_samples;
     const uint32_t *base = reinterpret_cast<const uint32_t *>(panel) + (active ? i : 0);
     const int64_t gw = s16_stride >> 2;                        // words per group
+    // accumulate: y holds the sums over the causal rows of earlier panels (batched runs): the per-sample chain of
+    // additions simply continues, so the result is bit-identical to one pass over all rows
     double acc[K];
 #pragma unroll
-    for (int k = 0; k < K; k++) acc[k] = 0.0;
+    for (int k = 0; k < K; k++) acc[k] = (accumulate && active) ? (k == 0 ? y1[i] : y2[i]) : 0.0;
 
     uint32_t w[4], wn[4];
 #pragma unroll
@@ -290,16 +292,16 @@ int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, co
 }
 
 int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
-                           double *d_y1, double *d_y2)
+                           double *d_y1, double *d_y2, int accumulate)
 {
     const int64_t blocks = (ctx->n_samples + kThreads - 1) / kThreads;
     const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
     if (d_x2 && d_y2)
         pheno_exact_s16_kernel<2><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(ctx->panel, ctx->s16_stride, mc, ctx->n_samples,
-                                                                                  d_freq, d_x1, d_x2, d_y1, d_y2);
+                                                                                  d_freq, d_x1, d_x2, d_y1, d_y2, accumulate);
     else
         pheno_exact_s16_kernel<1><<<(unsigned)blocks, kThreads, 0, ctx->stream>>>(ctx->panel, ctx->s16_stride, mc, ctx->n_samples,
-                                                                                  d_freq, d_x1, nullptr, d_y1, nullptr);
+                                                                                  d_freq, d_x1, nullptr, d_y1, nullptr, accumulate);
     prof_end(ctx, ps);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_exact_s16_kernel launch");

@@ -581,7 +581,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 template <int K>
 __global__ void __launch_bounds__(256)
 tc_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int slots, const TcScale *__restrict__ scale,
-                 double *__restrict__ y1, double *__restrict__ y2)
+                 double *__restrict__ y1, double *__restrict__ y2, int accumulate)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -590,6 +590,7 @@ tc_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int 
         double s = 0.0;
         for (int q = 0; q < slots; q++) s += ypart[((int64_t)q * K + k) * npad + i];
         s += scale[k].constant;
+        if (accumulate) s += (k == 0) ? y1[i] : y2[i];
         if (k == 0) y1[i] = s; else y2[i] = s;
     }
 }
@@ -622,7 +623,7 @@ int make_panel_map(simu_b200_ctx *ctx, CUtensorMap *map)
 
 template <int K>
 int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2, double *d_y1,
-           double *d_y2)
+           double *d_y2, int accumulate)
 {
     const int64_t n = ctx->n_samples;
     const int64_t tiles = (n + kTile - 1) / kTile;
@@ -670,7 +671,7 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     pheno_tc_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p, map);
     prof_end(ctx, ps);
     ps = prof_begin(ctx, PROF_LUT_REDUCE);
-    tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2);
+    tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2, accumulate);
     prof_end(ctx, ps);
     ctx->launches += 3;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_tc launch");
@@ -679,13 +680,14 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
 }  // namespace
 
 int launch_pheno_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
-                    double *d_y1, double *d_y2)
+                    double *d_y1, double *d_y2, int accumulate)
 {
+    if (mc <= 0 && accumulate) return SIMU_B200_OK;
     if (mc <= 0) {   // source.cc:962-966: phenotypes start at zero
         CUDA_TRY(ctx, cudaMemsetAsync(d_y1, 0, (size_t)ctx->n_samples * sizeof(double), ctx->stream));
         if (d_y2) CUDA_TRY(ctx, cudaMemsetAsync(d_y2, 0, (size_t)ctx->n_samples * sizeof(double), ctx->stream));
         return SIMU_B200_OK;
     }
-    if (d_x2 && d_y2) return run_tc<2>(ctx, mc, d_freq, d_x1, d_x2, d_y1, d_y2);
-    return run_tc<1>(ctx, mc, d_freq, d_x1, nullptr, d_y1, nullptr);
+    if (d_x2 && d_y2) return run_tc<2>(ctx, mc, d_freq, d_x1, d_x2, d_y1, d_y2, accumulate);
+    return run_tc<1>(ctx, mc, d_freq, d_x1, nullptr, d_y1, nullptr, accumulate);
 }

@@ -545,24 +545,58 @@ struct Gpu {
             at += mc / D + (d < mc % D ? 1 : 0);
             hi[d] = at;
         }
-        for_each_gpu([&](size_t d) {
-            simu_b200_ctx *c = ctxs[d];
-            // compact causal panel (only the rows pio_next_row would read), sample-major in groups of sixteen rows:
-            // the layout of the tensor-core FAST kernel, of the ordered EXACT kernel and of the vertical counts
-            check(c, simu_b200_panel_alloc_layout(c, std::max<size_t>(1, hi[d] - lo[d]), SIMU_B200_LAYOUT_SAMPLE16));
-            size_t pos = lo[d];
-            int64_t dst = 0;
-            for (size_t f = 0; f < pio.num_files() && pos < hi[d]; f++) {
-                const int flo = pio.offset(f), fhi = flo + pio.file(f).num_loci();
-                std::vector<int64_t> local;
-                while (pos < hi[d] && causal[pos] < fhi) local.push_back(causal[pos++] - flo);
-                if (local.empty()) continue;
-                check(c, simu_b200_panel_load_bed(c, (pio.file(f).prefix + ".bed").c_str(), pio.file(f).num_loci(), local.data(),
-                                                  (int64_t)local.size(), dst));
-                dst += (int64_t)local.size();
-            }
-        });
+        // A GPU's slice normally fits its HBM as ONE panel, staged once and read by both passes.  When it does
+        // not (e.g. --causal-pi 1 on 11M variants x 100K samples = 275 GB on one GPU) the slice is cut into
+        // panel-sized batches that are staged again for the second pass -- the reference reads the .bed twice
+        // as well (source.cc:1235, :1295) -- so memory, not the command line, decides how a run is laid out.
+        files = &pio;
+        batches.assign(D, {});
+        for (size_t d = 0; d < D; d++) {
+            int64_t free_b = 0, total_b = 0;
+            check(ctxs[d], simu_b200_mem_info(ctxs[d], &free_b, &total_b));
+            const int64_t per_group = simu_b200_panel_bytes(ctxs[d], 16, SIMU_B200_LAYOUT_SAMPLE16);
+            // headroom: staging buffers, per-sample vectors and 64 B per causal row of weights / frequencies / effects
+            int64_t budget = free_b - (int64_t(1) << 30) - 64 * (int64_t)(hi[d] - lo[d]) - 64 * (int64_t)o.num_samples;
+            if (const char *cap = getenv("SIMU_B200_MAX_PANEL_MB")) budget = std::min<int64_t>(budget, (int64_t)atoll(cap) << 20);
+            const size_t max_rows = (size_t)std::max<int64_t>(1, budget / per_group) * 16;
+            for (size_t at = lo[d]; at < hi[d]; at += max_rows) batches[d].push_back({at, std::min(hi[d], at + max_rows)});
+            if (batches[d].empty()) batches[d].push_back({lo[d], hi[d]});
+        }
+        loaded.assign(D, (size_t)-1);
+        if (resident()) for_each_gpu([&](size_t d) { load(d, 0); });
     }
+    bool resident() const
+    {
+        for (const auto &b : batches) if (b.size() != 1) return false;
+        return true;
+    }
+    // stage batch b of GPU d's slice into its panel (compact causal panel: only the rows pio_next_row would read,
+    // sample-major in groups of sixteen rows -- the layout of the vertical counts and of both find_pheno kernels)
+    void load(size_t d, size_t b)
+    {
+        if (loaded[d] == b) return;
+        simu_b200_ctx *c = ctxs[d];
+        const size_t blo = batches[d][b].first, bhi = batches[d][b].second;
+        size_t largest = 1;
+        for (const auto &r : batches[d]) largest = std::max(largest, r.second - r.first);
+        if ((size_t)simu_b200_panel_rows(c) < largest || simu_b200_panel_layout(c) != SIMU_B200_LAYOUT_SAMPLE16)
+            check(c, simu_b200_panel_alloc_layout(c, (int64_t)largest, SIMU_B200_LAYOUT_SAMPLE16));
+        size_t pos = blo;
+        int64_t dst = 0;
+        for (size_t f = 0; f < files->num_files() && pos < bhi; f++) {
+            const int flo = files->offset(f), fhi = flo + files->file(f).num_loci();
+            std::vector<int64_t> local;
+            while (pos < bhi && causal[pos] < fhi) local.push_back(causal[pos++] - flo);
+            if (local.empty()) continue;
+            check(c, simu_b200_panel_load_bed(c, (files->file(f).prefix + ".bed").c_str(), files->file(f).num_loci(), local.data(),
+                                              (int64_t)local.size(), dst));
+            dst += (int64_t)local.size();
+        }
+        loaded[d] = b;
+    }
+    const PlinkFiles *files = nullptr;
+    std::vector<std::vector<std::pair<size_t, size_t>>> batches;      // per GPU: ranges of `causal`, one panel each
+    std::vector<size_t> loaded;                                       // per GPU: the batch its panel holds
 };
 
 void find_freq(const SimuOptions &o, const std::vector<int> &comp, const PlinkFiles &pio, Gpu &gpu,
@@ -573,9 +607,12 @@ void find_freq(const SimuOptions &o, const std::vector<int> &comp, const PlinkFi
     if (gpu.causal.empty()) return;
     std::vector<double> f(gpu.causal.size());
     gpu.for_each_gpu([&](size_t d) {
-        if (gpu.hi[d] > gpu.lo[d])
-            Gpu::check(gpu.ctxs[d], simu_b200_find_freq(gpu.ctxs[d], nullptr, (int64_t)(gpu.hi[d] - gpu.lo[d]), nullptr,
-                                                        f.data() + gpu.lo[d]));
+        for (size_t b = 0; b < gpu.batches[d].size(); b++) {
+            const size_t l = gpu.batches[d][b].first, n = gpu.batches[d][b].second - l;
+            if (!n) continue;
+            gpu.load(d, b);
+            Gpu::check(gpu.ctxs[d], simu_b200_find_freq(gpu.ctxs[d], nullptr, (int64_t)n, nullptr, f.data() + l));
+        }
     });
     for (size_t j = 0; j < gpu.causal.size(); j++) (*freq_vec)[gpu.causal[j]] = f[j];
 }
@@ -596,20 +633,32 @@ void find_pheno(const SimuOptions &o, const std::vector<double> &freq_vec, const
     if (bivariate) pheno2->assign(o.num_samples, 0.0);
     const int mode = find_pheno_mode();
     const size_t D = gpu.ctxs.size();
+    // the rows of one GPU, batch by batch in ascending order, summed into (q1, q2): one call when the slice is
+    // resident, else one panel load + accumulate per batch (EXACT: the per-sample chain of additions continues)
+    auto run = [&](size_t d, double *q1, double *q2) {
+        if (gpu.batches[d].size() == 1) {
+            const size_t l = gpu.lo[d], n = gpu.hi[d] - l;
+            gpu.load(d, 0);
+            Gpu::check(gpu.ctxs[d], simu_b200_find_pheno(gpu.ctxs[d], nullptr, (int64_t)n, f.data() + l, x1.data() + l,
+                                                         bivariate ? x2.data() + l : nullptr, q1, bivariate ? q2 : nullptr, mode));
+            return;
+        }
+        for (size_t b = 0; b < gpu.batches[d].size(); b++) {
+            const size_t l = gpu.batches[d][b].first, n = gpu.batches[d][b].second - l;
+            gpu.load(d, b);
+            Gpu::check(gpu.ctxs[d], simu_b200_find_pheno_accumulate(gpu.ctxs[d], (int64_t)n, f.data() + l, x1.data() + l,
+                                                                    bivariate ? x2.data() + l : nullptr, q1,
+                                                                    bivariate ? q2 : nullptr, mode));
+        }
+    };
     if (D == 1) {
-        gpu.check(simu_b200_find_pheno(gpu.ctx, nullptr, (int64_t)mc, f.data(), x1.data(), bivariate ? x2.data() : nullptr,
-                                       pheno1->data(), bivariate ? pheno2->data() : nullptr, mode));
+        run(0, pheno1->data(), bivariate ? pheno2->data() : nullptr);
         return;
     }
     // one partial N x K phenotype per GPU, summed in device order (the path's one exchange step)
     std::vector<std::vector<double>> p1(D, std::vector<double>(o.num_samples, 0.0)), p2(D);
     if (bivariate) for (auto &v : p2) v.assign(o.num_samples, 0.0);
-    gpu.for_each_gpu([&](size_t d) {
-        const size_t l = gpu.lo[d], n = gpu.hi[d] - l;
-        Gpu::check(gpu.ctxs[d], simu_b200_find_pheno(gpu.ctxs[d], nullptr, (int64_t)n, f.data() + l, x1.data() + l,
-                                                     bivariate ? x2.data() + l : nullptr, p1[d].data(),
-                                                     bivariate ? p2[d].data() : nullptr, mode));
-    });
+    gpu.for_each_gpu([&](size_t d) { run(d, p1[d].data(), bivariate ? p2[d].data() : nullptr); });
     for (size_t d = 0; d < D; d++)
         for (int i = 0; i < o.num_samples; i++) {
             (*pheno1)[i] += p1[d][i];

@@ -26,10 +26,11 @@ CLI = os.path.join(ROOT, "simu_b200", "bin", "simu_b200")
 F32 = np.float32
 
 
-def run(args, cwd, mode="fast", devices=None):
+def run(args, cwd, mode="fast", devices=None, extra_env=None):
     env = dict(os.environ, SIMU_B200_MODE=mode)
     if devices:
         env["SIMU_B200_DEVICES"] = devices
+    env.update(extra_env or {})
     p = subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True, timeout=600, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     return p.stdout
@@ -205,6 +206,76 @@ def test_snp_sharding_over_several_contexts(tmp_path, devices):
                 assert close([r[c] for r in b2], [r[c] for r in b1], rtol=1e-5 if mode == "fast" else 1e-12)
     # more contexts than causal variants: empty slices are fine
     run(["--bfile", "c1", "--qt", "--causal-n", "2", "--seed", "1", "--out", "tiny"], tmp_path, "fast", devices="0,0,0")
+
+
+def test_causal_rows_larger_than_hbm_run_in_batches(tmp_path):
+    """A causal set that does not fit the GPU (here: SIMU_B200_MAX_PANEL_MB=1 against 3.5 MB of causal rows, three
+    bfiles, slices and batches crossing file boundaries) is staged panel by panel for each of the two passes, as
+    the reference streams it from disk (source.cc:1235, :1295).  EXACT mode continues every sample's chain of FP64
+    additions across batches: the outputs are byte-identical to the resident run.  FAST mode adds per-batch sums."""
+    n = 30_011
+    sizes = {"1": 170, "2": 90, "3": 211}
+    rows = oracle.synth_rows(20240901, 0, sum(sizes.values()), n)
+    off = 0
+    for lab, sz in sizes.items():
+        plink.write_fileset(str(tmp_path / f"c{lab}"), rows[off:off + sz], n, chromosome=int(lab), first_index=off)
+        off += sz
+    args = ["--bfile-chr", "c@", "--chr-labels", "1", "2", "3", "--qt", "--num-traits", "2", "--rg", "0.3", "--gcta-sigma",
+            "--causal-pi", "1.0", "--hsq", "0.6", "0.4", "--seed", "5"]
+    small = {"SIMU_B200_MAX_PANEL_MB": "1"}                         # 16-row groups of 120 KB: 8 groups = 128 rows per batch
+    for mode in ("exact", "fast"):
+        run(args + ["--out", f"res_{mode}"], tmp_path, mode)
+        run(args + ["--out", f"bat_{mode}"], tmp_path, mode, extra_env=small)
+        run(args + ["--out", f"bat3_{mode}"], tmp_path, mode, devices="0,0,0", extra_env=small)
+        for ext in (".pheno", ".1.causals", ".2.causals"):
+            a = open(tmp_path / f"res_{mode}{ext}").read()
+            b = open(tmp_path / f"bat_{mode}{ext}").read()
+            if mode == "exact":
+                assert a == b, ext                                   # bit-identical sums -> identical text
+            h1, b1 = read_table(tmp_path / f"res_{mode}{ext}")
+            for other in ("bat", "bat3"):
+                h2, b2 = read_table(tmp_path / f"{other}_{mode}{ext}")
+                first_num = 2 if ext == ".pheno" else 5
+                assert h1 == h2 and [r[:first_num] for r in b1] == [r[:first_num] for r in b2]
+                for c in range(first_num, len(h1)):
+                    assert close([r[c] for r in b2], [r[c] for r in b1], rtol=1e-9)
+
+
+def test_unknown_mode_is_an_error_and_default_is_exact(fileset):
+    d, rows, n, m = fileset
+    args = ["--bfile", "syn", "--qt", "--causal-n", "50", "--hsq", "0.5", "--seed", "1"]
+    env = {k: v for k, v in os.environ.items() if k != "SIMU_B200_MODE"}
+    p = subprocess.run([CLI] + args + ["--out", "dflt"], cwd=d, capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0 and "simu_b200: find_pheno mode exact, 1 GPU" in p.stdout
+    assert "simu_b200: find_pheno mode exact" in open(d / "dflt.log").read()
+    run(args + ["--out", "expl"], d, "exact")
+    assert open(d / "dflt.pheno").read() == open(d / "expl.pheno").read()
+    for bad in ("EXACT", "fsat", "1"):
+        p = subprocess.run([CLI] + args + ["--out", "bad"], cwd=d, capture_output=True, text=True, timeout=600,
+                           env=dict(env, SIMU_B200_MODE=bad))
+        assert p.returncode == 1 and f"SIMU_B200_MODE must be 'exact' or 'fast', got '{bad}'" in p.stdout
+
+
+def test_v099_bed_header_is_accepted_and_sample_major_refused(fileset, tmp_path):
+    """libplinkio/src/bed_header.c:56-102: a v0.99 file starts with ONE order byte (01 = one locus per row) and its data
+    at offset 1; the reference runs it.  Order byte 00 (one sample per row), v1.00 or v0.99, is refused with the
+    reference's text (source.cc:196-200)."""
+    d, rows, n, m = fileset
+    B = (n + 3) // 4
+    body = rows[:, :B].tobytes()
+    for name, header in (("v100", bytes([0x6C, 0x1B, 0x01])), ("v099", bytes([0x01]))):
+        for ext in (".bim", ".fam"):
+            (tmp_path / f"{name}{ext}").write_bytes((d / f"syn{ext}").read_bytes())
+        (tmp_path / f"{name}.bed").write_bytes(header + body)
+        run(["--bfile", name, "--qt", "--causal-n", "60", "--seed", "3", "--out", name], tmp_path, "exact")
+    assert open(tmp_path / "v100.pheno").read() == open(tmp_path / "v099.pheno").read()
+    assert open(tmp_path / "v100.1.causals").read() == open(tmp_path / "v099.1.causals").read()
+    for name, header in (("s100", bytes([0x6C, 0x1B, 0x00])), ("s099", bytes([0x00])), ("pre", bytes([0x7F]))):
+        for ext in (".bim", ".fam"):
+            (tmp_path / f"{name}{ext}").write_bytes((d / f"syn{ext}").read_bytes())
+        (tmp_path / f"{name}.bed").write_bytes(header + body)
+        p = subprocess.run([CLI, "--bfile", name, "--qt", "--out", name], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 1 and f"ERROR: Unsupported format in {name}, snps must be rows, samples must be columns" in p.stdout
 
 
 def test_causal_regions_and_components(fileset):
