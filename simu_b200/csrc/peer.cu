@@ -7,6 +7,13 @@
 // exchange safe without a trailing barrier: a rank can only write buffer e & 1 again after the
 // all-reduce of epoch e+1, which needs every rank's flag for e+1, which is raised after that
 // rank's reads of epoch e.
+//
+// With more than two ranks the one-shot form reads (world - 1) x the payload per rank (8 ranks, 1.6 MB:
+// 35 us against NCCL's 30).  The TWO-SHOT form below moves 2 (world - 1) / world of it: every rank
+// sums ITS 1/world slice of the samples out of the peers' partials (reduce-scatter), publishes the
+// reduced slice, and gathers the peers' slices (all-gather) -- still one cooperative launch, two
+// flag rounds, sums in rank order, the same bits on every rank.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -19,9 +26,43 @@ namespace {
 constexpr int kMaxPeers = 16;
 
 struct PeerPtrs {
-    const double *buf[kMaxPeers];      // each rank's symmetric buffer: [2][count]
-    uint32_t *flags[kMaxPeers];        // each rank's flag block:       [2][kMaxPeers]
+    const double *buf[kMaxPeers];      // each rank's symmetric buffer: partials [2][count], then reduced slices [2][count]
+    uint32_t *flags[kMaxPeers];        // each rank's flag block:       [2 rounds][2][kMaxPeers]
 };
+
+__device__ __forceinline__ void grid_barrier_sys(uint32_t *barrier, uint32_t target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd(barrier, 1u);
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+// raise flag `round` of this rank's epoch in every peer's memory, then wait for every peer's
+__device__ __forceinline__ void flag_round(const PeerPtrs &pp, int round, int rank, int world, int parity, uint32_t epoch)
+{
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[threadIdx.x] + (round * 2 + parity) * kMaxPeers + rank), "r"(epoch)
+                     : "memory");
+    }
+    if (threadIdx.x < world) {                      // my flag block is written by the peers over NVLink
+        const uint32_t *f = pp.flags[rank] + (round * 2 + parity) * kMaxPeers + threadIdx.x;
+        uint32_t v;
+        const long long t0 = clock64();
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (clock64() - t0 > 20000000000ll) __trap();      // a peer died: fail, do not hang
+        } while (v < epoch);
+    }
+    __syncthreads();
+}
 
 // publish -> grid barrier -> flag the peers -> wait for their flags -> sum, as ONE cooperative launch
 // (three separate launches cost ~16 us of launch latency for ~5 us of work)
@@ -34,31 +75,8 @@ peer_allreduce_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t epo
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = first; i < count; i += stride) mine[i] = y[i];
     // grid barrier: every block's part of the partial is written (system scope: the peers will read it)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        atomicAdd(barrier, 1u);
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(barrier) : "memory");
-        } while (v < barrier_target);
-    }
-    __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x < world) {   // tell every peer that epoch `epoch` of this rank is readable
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[threadIdx.x] + parity * kMaxPeers + rank), "r"(epoch)
-                     : "memory");
-    }
-    if (threadIdx.x < world) {                      // my flag block is written by the peers over NVLink
-        const uint32_t *f = pp.flags[rank] + parity * kMaxPeers + threadIdx.x;
-        uint32_t v;
-        const long long t0 = clock64();
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (clock64() - t0 > 20000000000ll) __trap();      // a peer died: fail, do not hang
-        } while (v < epoch);
-    }
-    __syncthreads();
+    grid_barrier_sys(barrier, barrier_target);
+    flag_round(pp, 0, rank, world, parity, epoch);
     // pairs of doubles (the buffers are 16-byte aligned when count is even), all peers' loads in flight at once;
     // rank order of the adds: the same bits on every rank
     const int64_t pairs = ((count & 1) || (reinterpret_cast<uintptr_t>(y) & 15)) ? 0 : count / 2;
@@ -88,6 +106,48 @@ peer_allreduce_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t epo
     }
 }
 
+// two-shot: publish | barrier | flags A | reduce my slice from all partials | barrier | flags B | gather the slices.
+// count2 = count / 2 pairs of doubles (the host routes odd counts and unaligned y to the one-shot kernel).
+__global__ void __launch_bounds__(kPeerThreads)
+peer_allreduce2_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t epoch, int64_t count, double *__restrict__ y,
+                       double *__restrict__ mine, double *__restrict__ my_slices, uint32_t *barrier, uint32_t barrier_target)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t pairs = count / 2;
+    for (int64_t i = first; i < pairs; i += stride) reinterpret_cast<double2 *>(mine)[i] = reinterpret_cast<const double2 *>(y)[i];
+    grid_barrier_sys(barrier, barrier_target - gridDim.x);
+    flag_round(pp, 0, rank, world, parity, epoch);
+    // reduce-scatter: pairs [lo, hi) are this rank's; every peer's partial is read for that slice only
+    const int64_t lo = pairs * rank / world, hi = pairs * (rank + 1) / world;
+    for (int64_t i = lo + first; i < hi; i += stride) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int r0 = 0; r0 < world; r0 += 8) {
+            double a[8], b[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (r0 + q < world)
+                    asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(a[q]), "=d"(b[q])
+                                 : "l"(pp.buf[r0 + q] + (int64_t)parity * count + 2 * i));
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (r0 + q < world) { s0 += a[q]; s1 += b[q]; }
+        }
+        reinterpret_cast<double2 *>(my_slices)[i] = make_double2(s0, s1);
+        reinterpret_cast<double2 *>(y)[i] = make_double2(s0, s1);
+    }
+    grid_barrier_sys(barrier, barrier_target);
+    flag_round(pp, 1, rank, world, parity, epoch);
+    // all-gather: the peers' reduced slices, straight into y
+    for (int64_t i = first; i < pairs; i += stride) {
+        if (i >= lo && i < hi) continue;
+        int owner = (int)(((i + 1) * world - 1) / pairs);          // largest r with pairs * r / world <= i
+        double a, b;
+        asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(a), "=d"(b)
+                     : "l"(pp.buf[owner] + (int64_t)(2 + parity) * count + 2 * i));
+        reinterpret_cast<double2 *>(y)[i] = make_double2(a, b);
+    }
+}
+
 }  // namespace
 
 struct simu_b200_peer {
@@ -102,7 +162,7 @@ struct simu_b200_peer {
     bool connected = false;
 };
 
-static size_t sym_bytes(int64_t count) { return (size_t)2 * count * sizeof(double) + 2 * kMaxPeers * sizeof(uint32_t); }
+static size_t sym_bytes(int64_t count) { return (size_t)4 * count * sizeof(double) + 4 * kMaxPeers * sizeof(uint32_t); }
 
 extern "C" {
 
@@ -146,7 +206,7 @@ int simu_b200_peer_connect(simu_b200_ctx *ctx, const void *handles)
             p->peer_base[r] = base;
         }
         p->pp.buf[r] = (const double *)base;
-        p->pp.flags[r] = (uint32_t *)((char *)base + (size_t)2 * p->count * sizeof(double));
+        p->pp.flags[r] = (uint32_t *)((char *)base + (size_t)4 * p->count * sizeof(double));
     }
     p->connected = true;
     return SIMU_B200_OK;
@@ -161,11 +221,22 @@ int simu_b200_peer_allreduce_dev(simu_b200_ctx *ctx, double *d_y, int64_t count)
     const uint32_t epoch = ++p->epoch;
     const int parity = (int)(epoch & 1u);
     int blocks = (int)std::min<int64_t>((count + 2 * kPeerThreads - 1) / (2 * kPeerThreads), (int64_t)ctx->num_sms);   // co-resident
-    p->barrier_target += (uint32_t)blocks;
     double *mine = p->sym + (int64_t)parity * count;
-    void *args[] = {(void *)&p->pp, (void *)&p->rank, (void *)&p->world, (void *)&parity, (void *)&epoch, (void *)&count,
-                    (void *)&d_y, (void *)&mine, (void *)&p->barrier, (void *)&p->barrier_target};
-    CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)peer_allreduce_kernel, dim3((unsigned)blocks), dim3(kPeerThreads), args, 0, ctx->stream));
+    // more than two ranks: two-shot (reduce-scatter + all-gather), which moves 2 (world-1)/world of the payload per
+    // rank instead of (world-1) x; SIMU_B200_PEER_ONESHOT=1 forces the one-shot form (A/B runs)
+    const bool two_shot = p->world > 2 && !(count & 1) && !(reinterpret_cast<uintptr_t>(d_y) & 15) && !getenv("SIMU_B200_PEER_ONESHOT");
+    if (two_shot) {
+        p->barrier_target += 2u * (uint32_t)blocks;
+        double *slices = p->sym + (int64_t)(2 + parity) * count;
+        void *args[] = {(void *)&p->pp, (void *)&p->rank, (void *)&p->world, (void *)&parity, (void *)&epoch, (void *)&count,
+                        (void *)&d_y, (void *)&mine, (void *)&slices, (void *)&p->barrier, (void *)&p->barrier_target};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)peer_allreduce2_kernel, dim3((unsigned)blocks), dim3(kPeerThreads), args, 0, ctx->stream));
+    } else {
+        p->barrier_target += (uint32_t)blocks;
+        void *args[] = {(void *)&p->pp, (void *)&p->rank, (void *)&p->world, (void *)&parity, (void *)&epoch, (void *)&count,
+                        (void *)&d_y, (void *)&mine, (void *)&p->barrier, (void *)&p->barrier_target};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)peer_allreduce_kernel, dim3((unsigned)blocks), dim3(kPeerThreads), args, 0, ctx->stream));
+    }
     ctx->launches += 1;
     return ctx_cuda(ctx, cudaGetLastError(), "peer_allreduce launch");
 }

@@ -14,7 +14,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dev = torch.device("cuda", local)
 bad = 0
-for n, k in ((100_000, 2), (100_000, 1), (500_000, 2), (1, 1), (12_345, 2)):
+for n, k in ((100_000, 2), (100_000, 1), (500_000, 2), (1, 1), (12_345, 2), (33_333, 1), (7, 2)):
     count = n * k
     ctx = capi.Context(max(n, 4), device=local)
     stream = torch.cuda.Stream(device=dev)
