@@ -468,6 +468,20 @@ def run_ours(args, w):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; simu_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # bind this rank to the CPUs closest to its GPU BEFORE any pinned host memory is allocated: the staging
+    # buffers of the e2e leg are then first touched on the GPU's NUMA node (8 ranks sharing one node's memory
+    # controllers halve the per-GPU host->device rate; tools/h2d_probe.py measures both placements)
+    affinity = "unchanged"
+    if not args.no_affinity:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+            affinity = f"NVML ideal CPUs of GPU {phys} ({len(os.sched_getaffinity(0))} of {os.cpu_count()})"
+        except Exception as e:      # noqa: BLE001
+            affinity = f"unchanged ({type(e).__name__})"
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -559,6 +573,7 @@ def run_ours(args, w):
     e2e = {"value": updates_step / (e2e_ms * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": e2e_steps,
            "staging_ms": stage_ms, "staging_gbs": mc * B / stage_ms / 1e6,
+           "host_cpu_affinity": affinity,
            "api": "simu_b200_panel_put_rows + find_freq + find_pheno + apply_heritability (host buffers)"}
     # the device-resident and host-buffer paths must agree (same inputs, same kernels)
     e2e_check = float(np.abs(e2e_y[0]).sum() + (np.abs(e2e_y[1]).sum() if k == 2 else 0.0))
@@ -664,6 +679,7 @@ def main():
                          "in GROUP4 layout (lookup-table FAST kernel), or the whole .bed slice row-major with a causal row list")
     ap.add_argument("--graph", default="auto", choices=["auto", "off"],
                     help="single GPU: replay one CUDA graph of the step per timed iteration (auto) or launch eagerly (off)")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the process to the CPUs NVML names as closest to its GPU")
     ap.add_argument("--no-also", action="store_true", help="skip the `also` block (the other BASELINE configs)")
     ap.add_argument("--also-steps", type=int, default=0, help="steps per `also` workload (0: as many as fill ~60 ms)")
     ap.add_argument("--cc-sort", action="store_true",
