@@ -27,12 +27,12 @@
 namespace {
 
 constexpr int kWarps = 8;
-constexpr int kLevels = 29;        // counts up to 2^29 - 1 >= the largest N simu_b200_open accepts
+constexpr int kMaxLevels = 29;     // counts up to 2^29 - 1 >= the largest N simu_b200_open accepts
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *p)
 {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"     // not volatile: the scheduler may hoist the next round's loads
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
@@ -46,6 +46,7 @@ __device__ __forceinline__ void csa(uint32_t &sum, uint32_t &carry, uint32_t a, 
     sum = s; carry = m;
 }
 
+template <int kLevels>
 struct Sliced {
     uint32_t lvl[kLevels];
     __device__ __forceinline__ void clear()
@@ -104,9 +105,9 @@ struct Sliced {
 };
 
 // one round: vectors i0 + q*stride, q < 8 (zero beyond nvec when CHECKED) -> weight-32 words of both trees
-template <bool CHECKED>
-__device__ __forceinline__ void round32(const uint4 *__restrict__ p, int64_t i0, int64_t stride, int64_t nvec, Sliced &R,
-                                        Sliced &A, uint32_t &r32, uint32_t &a32)
+template <bool CHECKED, int NLEV>
+__device__ __forceinline__ void round32(const uint4 *__restrict__ p, int64_t i0, int64_t stride, int64_t nvec, Sliced<NLEV> &R,
+                                        Sliced<NLEV> &A, uint32_t &r32, uint32_t &a32)
 {
     uint4 v[8];
 #pragma unroll
@@ -120,11 +121,13 @@ __device__ __forceinline__ void round32(const uint4 *__restrict__ p, int64_t i0,
     for (int q = 0; q < 8; q++) { w[4 * q] = v[q].x; w[4 * q + 1] = v[q].y; w[4 * q + 2] = v[q].z; w[4 * q + 3] = v[q].w; }
 #pragma unroll
     for (int q = 0; q < 32; q++) b[q] = w[q] & (w[q] * 2u);
-    r32 = R.fold<0, 5, 0>(w);
-    a32 = A.fold<0, 5, 0>(b);
+    r32 = R.template fold<0, 5, 0>(w);
+    a32 = A.template fold<0, 5, 0>(b);
 }
 
-template <int SPLIT>
+// NLEV: levels of the bit-sliced counters = bits of the largest count, N < 2^NLEV (20 covers a million samples and
+// leaves the registers the scheduler needs to keep the next round's loads in flight)
+template <int SPLIT, int NLEV>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 counts_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int64_t mc, int64_t n_samples,
                   int32_t *__restrict__ counts, double *__restrict__ freq)
@@ -136,7 +139,7 @@ counts_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int64_t
     const int64_t nvec = (n_samples + 3) >> 2;                     // 16-byte vectors (4 samples) with data
     const int64_t stride = 32 * SPLIT;
     int nlev = 1;
-    while (nlev < kLevels && (n_samples >> nlev) != 0) nlev++;     // counts <= N < 2^nlev
+    while (nlev < NLEV && (n_samples >> nlev) != 0) nlev++;        // counts <= N < 2^nlev
     constexpr int kPerCta = kWarps / SPLIT;
 
     for (int64_t gb = (int64_t)blockIdx.x * kPerCta; gb < ngroups; gb += (int64_t)gridDim.x * kPerCta) {
@@ -148,23 +151,23 @@ counts_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int64_t
         uint32_t lo = 0, hi = 0, both = 0;
         if (g < ngroups) {
             const uint4 *p = reinterpret_cast<const uint4 *>(panel + g * s16_stride);
-            Sliced R, A;
+            Sliced<NLEV> R, A;
             R.clear(); A.clear();
             int64_t i0 = sub * 32 + lane;
             // super-rounds of 8 rounds = 256 words per lane
             for (; i0 + 63 * stride < nvec; i0 += 64 * stride) {
                 uint32_t r32[8], a32[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) round32<false>(p, i0 + 8 * r * stride, stride, nvec, R, A, r32[r], a32[r]);
-                R.ripple<8>(R.fold<5, 3, 0>(r32), nlev);
-                A.ripple<8>(A.fold<5, 3, 0>(a32), nlev);
+                for (int r = 0; r < 8; r++) round32<false, NLEV>(p, i0 + 8 * r * stride, stride, nvec, R, A, r32[r], a32[r]);
+                R.template ripple<8>(R.template fold<5, 3, 0>(r32), nlev);
+                A.template ripple<8>(A.template fold<5, 3, 0>(a32), nlev);
             }
             for (; i0 < nvec; i0 += 8 * stride) {
                 uint32_t r32, a32;
-                if (i0 + 7 * stride < nvec) round32<false>(p, i0, stride, nvec, R, A, r32, a32);
-                else round32<true>(p, i0, stride, nvec, R, A, r32, a32);
-                R.ripple<5>(r32, nlev);
-                A.ripple<5>(a32, nlev);
+                if (i0 + 7 * stride < nvec) round32<false, NLEV>(p, i0, stride, nvec, R, A, r32, a32);
+                else round32<true, NLEV>(p, i0, stride, nvec, R, A, r32, a32);
+                R.template ripple<5>(r32, nlev);
+                A.template ripple<5>(a32, nlev);
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) { R.add_lane(off, nlev); A.add_lane(off, nlev); }
@@ -213,9 +216,12 @@ int launch_counts_s16(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int32
     while (split < kWarps && groups * split < 8 * resident) split *= 2;
     int64_t blocks = (groups * split + kWarps - 1) / kWarps;
     if (blocks > max_blocks) blocks = max_blocks;
-#define LAUNCH_S16(S) counts_s16_kernel<S><<<(unsigned)blocks, kWarps * 32, 0, stream>>>( \
+#define LAUNCH_S16(S, L) counts_s16_kernel<S, L><<<(unsigned)blocks, kWarps * 32, 0, stream>>>( \
         ctx->panel, ctx->s16_stride, mc, ctx->n_samples, d_counts, d_freq)
-    if (split == 1) LAUNCH_S16(1); else if (split == 2) LAUNCH_S16(2); else if (split == 4) LAUNCH_S16(4); else LAUNCH_S16(8);
+#define LAUNCH_S16_L(L) do { if (split == 1) LAUNCH_S16(1, L); else if (split == 2) LAUNCH_S16(2, L); else if (split == 4) LAUNCH_S16(4, L); \
+                             else LAUNCH_S16(8, L); } while (0)
+    if (ctx->n_samples < (1 << 20)) LAUNCH_S16_L(20); else LAUNCH_S16_L(kMaxLevels);
+#undef LAUNCH_S16_L
 #undef LAUNCH_S16
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "counts_s16_kernel launch");
