@@ -373,7 +373,9 @@ class Workload:
                 dist.all_reduce(t, op=dist.ReduceOp.MIN)
                 steps = int(t.item())
         graph = None
-        if self.world == 1 and self.args.graph != "off":
+        # (EXACT mode is timed eagerly: its SAMPLE16 kernel takes the effects as kernel parameters fetched from the device at call
+        # time, which a stream capture does not allow -- under capture the library falls back to its slower table kernel)
+        if self.world == 1 and self.args.graph != "off" and self.mode == self.capi.MODE_FAST:
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.stream):

@@ -157,6 +157,7 @@ void simu_b200_close(simu_b200_ctx *ctx)
     for (int i = 0; i < 20; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (i == 0 && ctx->h_eff) cudaFreeHost(ctx->h_eff);
         if (ctx->dstage[i]) cudaFree(ctx->dstage[i]);
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         if (ctx->ev_repitch[i]) cudaEventDestroy(ctx->ev_repitch[i]);
@@ -748,8 +749,10 @@ static int find_pheno_host_impl(simu_b200_ctx *ctx, const int32_t *rows, int64_t
         if (pheno2) CUDA_TRY(ctx, cudaMemcpyAsync(d_y2, pheno2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    ctx->h_x1 = effect1; ctx->h_x2 = effect2;              // EXACT on SAMPLE16 passes them as kernel parameters
     rc = find_pheno_dev_impl(ctx, (const int32_t *)d_rows, mc, (const double *)d_freq, (const double *)d_x1,
                              (const double *)d_x2, d_y1, d_y2, mode, accumulate);
+    ctx->h_x1 = ctx->h_x2 = nullptr;
     if (rc) return rc;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(pheno1, d_y1, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -57,6 +57,11 @@ struct simu_b200_ctx {
     int coop_sort_blocks = -1;           // co-resident blocks of the cooperative sort (-1: not queried)
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
+    // EXACT mode on SAMPLE16 panels takes the effects from the kernel-parameter bank: host copies of the current call's
+    // effects (set by the host-buffer entry points for the duration of the call) or a pinned fetch buffer
+    const double *h_x1 = nullptr, *h_x2 = nullptr;
+    double *h_eff = nullptr;
+    size_t h_eff_bytes = 0;
     simu_b200_peer *peer = nullptr;          // multi-GPU exchange over NVLink peer memory (peer.cu)
     std::string err;
 };
