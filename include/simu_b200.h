@@ -312,6 +312,16 @@ SIMU_B200_API int simu_b200_peer_connect(simu_b200_ctx *ctx, const void *handles
 SIMU_B200_API int simu_b200_peer_allreduce_dev(simu_b200_ctx *ctx, double *d_y, int64_t count);
 SIMU_B200_API void simu_b200_peer_close(simu_b200_ctx *ctx);
 
+/* The missing-genotype index of a SAMPLE16 panel.  find_pheno's FAST kernel treats the missing genotypes -- the
+ * reference's `continue` (source.cc:991) -- as a sparse correction when a panel is used more than once: the list
+ * of missing entries (compressed by sample) is built at the SECOND FAST call after the panel changed (two scans of
+ * the panel; it depends on the panel only, like the layout), the first call runs with the dense plane of the MMA;
+ * from then on each call adds the entries' weights as exact 64-bit integers beside the main kernel.  *state: 0 = not
+ * built (fewer than two FAST calls since the panel changed), 1 = sparse list in use (*entries = its length), 2 =
+ * dense plane in use (more than 0.4 % missing genotypes, or SIMU_B200_TC_DENSE set).  Both forms give bit-identical
+ * results. */
+SIMU_B200_API int simu_b200_missing_index(const simu_b200_ctx *ctx, int *state, int64_t *entries);
+
 /* Device time in milliseconds of the last find_freq / find_pheno call on this
  * context, measured with CUDA events on the launching stream (kernels only;
  * 0 if none).  which: 0 = find_freq, 1 = find_pheno. */

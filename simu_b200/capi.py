@@ -69,6 +69,7 @@ SIGNATURES = {
     "simu_b200_peer_connect": (_i32, [_vp, _vp]),
     "simu_b200_peer_allreduce_dev": (_i32, [_vp, _vp, _i64]),
     "simu_b200_peer_close": (None, [_vp]),
+    "simu_b200_missing_index": (_i32, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "simu_b200_last_kernel_ms": (_i32, [_vp, _i32, C.POINTER(C.c_float)]),
     "simu_b200_profile_enable": (_i32, [_vp, _i32]),
     "simu_b200_profile_read": (_i32, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
@@ -150,6 +151,12 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.simu_b200_launch_count(self.h))
+
+    def missing_index(self):
+        """(state, entries): 0 not built, 1 sparse list of `entries` missing genotypes, 2 dense plane (simu_b200.h)."""
+        st, n = C.c_int(0), C.c_int64(0)
+        self._check(self.lib.simu_b200_missing_index(self.h, C.byref(st), C.byref(n)))
+        return st.value, n.value
 
     def last_kernel_ms(self, which: int) -> float:
         ms = C.c_float()

@@ -154,7 +154,7 @@ void simu_b200_close(simu_b200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->panel) cudaFree(ctx->panel);
-    for (int i = 0; i < 20; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int i = 0; i < 32; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     for (int i = 0; i < 2; i++) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (i == 0 && ctx->h_eff) cudaFreeHost(ctx->h_eff);
@@ -217,6 +217,14 @@ int simu_b200_profile_read(simu_b200_ctx *ctx, int kernel_id, float *total_ms, i
     return SIMU_B200_OK;
 }
 
+int simu_b200_missing_index(const simu_b200_ctx *ctx, int *state, int64_t *entries)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    if (state) *state = ctx->miss_state;
+    if (entries) *entries = ctx->miss_state == 1 ? ctx->miss_total : 0;
+    return SIMU_B200_OK;
+}
+
 int simu_b200_last_kernel_ms(simu_b200_ctx *ctx, int which, float *ms)
 {
     if (!ctx || !ms || which < 0 || which > 1) return SIMU_B200_EINVAL;
@@ -234,6 +242,7 @@ int simu_b200_panel_free(simu_b200_ctx *ctx)
     ctx->panel = nullptr;
     ctx->panel_rows = 0;
     ctx->panel_bytes = 0;
+    miss_index_invalidate(ctx);
     return SIMU_B200_OK;
 }
 

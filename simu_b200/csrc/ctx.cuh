@@ -41,8 +41,8 @@ struct simu_b200_ctx {
     bool dstage_used[2] = {false, false};
 
     // grow-on-demand device scratch
-    void *scratch[20] = {nullptr};
-    size_t scratch_bytes[20] = {0};
+    void *scratch[32] = {nullptr};
+    size_t scratch_bytes[32] = {0};
 
     // optional per-kernel device timing (CUDA events on the launching stream)
     bool prof_on = false;
@@ -62,13 +62,17 @@ struct simu_b200_ctx {
     const double *h_x1 = nullptr, *h_x2 = nullptr;
     double *h_eff = nullptr;
     size_t h_eff_bytes = 0;
+    // missing-genotype index of the SAMPLE16 panel (miss_index.cu): 0 = not built, 1 = sparse list ready, 2 = dense m plane
+    int miss_state = 0, miss_chunks = 1, miss_uses = 0;
+    int64_t miss_total = 0;
     simu_b200_peer *peer = nullptr;          // multi-GPU exchange over NVLink peer memory (peer.cu)
     std::string err;
 };
 
 enum ScratchSlot {
     SCR_ROWS = 0, SCR_COUNTS, SCR_FREQ, SCR_X1, SCR_X2, SCR_Y1, SCR_Y2, SCR_NOISE,
-    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG, SCR_TCW
+    SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG, SCR_TCW,
+    SCR_MISS_CNT, SCR_MISS_ENT, SCR_MISS_OFF, SCR_WMFIX, SCR_CORR
 };
 
 int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...);
@@ -104,6 +108,13 @@ int launch_pheno_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const 
                     double *d_y1, double *d_y2, int accumulate);
 int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d_x1, const double *d_x2,
                            double *d_y1, double *d_y2, int accumulate);
+
+// missing-genotype index of a SAMPLE16 panel and the correction pass over it.  miss_index.cu
+void miss_index_invalidate(simu_b200_ctx *ctx);
+int miss_index_ensure(simu_b200_ctx *ctx);          // 1 sparse index ready, 0 use the dense plane, < 0 -status
+int64_t miss_corr_stride(const simu_b200_ctx *ctx);
+bool miss_correct_accumulates(const simu_b200_ctx *ctx);
+int launch_miss_correct(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int traits, const long long *d_wm, unsigned long long *d_corr);
 
 // kernel (b), exact FP64 ordered mode.  pheno_exact.cu
 int launch_pheno_exact(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq,

@@ -35,6 +35,13 @@
 // Work is split over min(#SM, steps) persistent CTAs exactly as in pheno_lut.cu (contiguous ranges of the
 // (tile, block) step list, rotated start, per-(CTA, tile) FP64 slots added in a fixed order).
 //
+// The m plane is SPARSE (missing genotypes only).  When the panel's missing-genotype index is available
+// (miss_index.cu: a list of the missing entries built once per panel) the kernel runs WITHOUT the m plane --
+// K = 32 bytes then cover the c planes of two groups, half the tensor-memory traffic and half the MMAs -- and
+// miss_correct_kernel adds sum_j Wm_j m_ij from the list as exact 64-bit integers in the same quantum: the same
+// fixed-point sum, bit for bit (config 2: 0.547 -> 0.375 ms + 0.03 ms).  DENSE = true keeps the plane (index not
+// applicable or more than 0.4 % missing).
+//
 // Algorithmic bytes: Mc (ceil(N/4) + 12 + 8K) + 8NK.
 #include <cuda.h>
 #include <math.h>
@@ -114,6 +121,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
                  "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
                  "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
 {
@@ -230,9 +243,22 @@ tc_prepare_kernel(const double *__restrict__ freq, const double *__restrict__ x1
 // plane, trait) to fixed point ONCE and writes all eight digit columns of that trait (128 bytes).
 template <int K>
 __device__ __forceinline__ void weight_item(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
-                                            int64_t mc, const double (&inv_quantum)[2], uint8_t *__restrict__ wt, int64_t blk, int t)
+                                            int64_t mc, const double (&inv_quantum)[2], uint8_t *__restrict__ wt, int64_t blk, int t,
+                                            long long *__restrict__ wm_fix /* sparse m plane: [mc][K] weights in quanta, else NULL */)
 {
     const int q = t & 3, plane = (t >> 2) & 1, k = t >> 3;
+    if (wm_fix && plane == 1) {           // the m plane is a list: its weights stay whole numbers of quanta
+#pragma unroll
+        for (int f = 0; f < 16; f++) {
+            const int64_t j = blk * kStepSnps + 16 * q + f;
+            if (j < mc) {
+                double wp, wm, c;
+                weights_of(freq[j], k == 0 ? x1[j] : x2[j], wp, wm, c);
+                wm_fix[j * K + k] = __double2ll_rn(wm * inv_quantum[k]);
+            }
+        }
+        return;
+    }
     uint32_t out[8][4];
 #pragma unroll
     for (int d = 0; d < 8; d++)
@@ -256,7 +282,11 @@ __device__ __forceinline__ void weight_item(const double *__restrict__ freq, con
         }
     }
     // sub-tile q at q*512; element (n, kappa): (kappa / 16) * 256 + (n / 8) * 128 + (n % 8) * 16 + kappa % 16, n = 8 k + d
-    uint4 *dst = reinterpret_cast<uint4 *>(wt + blk * kWTileBytes + q * 512 + plane * 256 + k * 128);
+    // sparse m plane: an MMA's 32 K bytes are the c planes of TWO groups -- group G = 4 (blk & 1) + q of the 128-SNP
+    // stage goes to sub-tile G / 2, K half G % 2 (2 KB of tiles per stage instead of 4 KB)
+    const int G = 4 * (int)(blk & 1) + q;
+    uint4 *dst = wm_fix ? reinterpret_cast<uint4 *>(wt + (blk >> 1) * (kHalves * kWTileBytes / 2) + (G >> 1) * 512 + (G & 1) * 256 + k * 128)
+                        : reinterpret_cast<uint4 *>(wt + blk * kWTileBytes + q * 512 + plane * 256 + k * 128);
 #pragma unroll
     for (int d = 0; d < 8; d++) dst[d] = make_uint4(out[d][0], out[d][1], out[d][2], out[d][3]);
     if (K == 1) {                                                   // the second trait's columns are zero
@@ -269,11 +299,11 @@ constexpr int kWeightItems = 16;        // per 64-SNP block: 4 groups x 2 planes
 template <int K>
 __global__ void __launch_bounds__(128)
 tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
-                  int64_t ntiles, const TcScale *__restrict__ scale, uint8_t *__restrict__ wt)
+                  int64_t ntiles, const TcScale *__restrict__ scale, uint8_t *__restrict__ wt, long long *__restrict__ wm_fix)
 {
     const double inv_quantum[2] = {ldexp(1.0, -scale[0].exponent), K == 2 ? ldexp(1.0, -scale[1].exponent) : 0.0};
     const int64_t item = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (item < ntiles * (8 * K)) weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)));
+    if (item < ntiles * (8 * K)) weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)), wm_fix);
 }
 
 // both passes in ONE CTA for small causal sets (the sparse configs are launch-bound: two dependent launches and a
@@ -283,7 +313,7 @@ constexpr int kSmallThreads = 1024, kSmallMc = 4096;
 template <int K>
 __global__ void __launch_bounds__(kSmallThreads)
 tc_small_prepare_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
-                        int64_t ntiles, TcScale *__restrict__ scale, uint8_t *__restrict__ wt)
+                        int64_t ntiles, TcScale *__restrict__ scale, uint8_t *__restrict__ wt, long long *__restrict__ wm_fix)
 {
     __shared__ double ssum[K][kSmallThreads], smax[K][kSmallThreads];
     __shared__ int sexp[2];
@@ -325,7 +355,7 @@ tc_small_prepare_kernel(const double *__restrict__ freq, const double *__restric
     __syncthreads();
     const double inv_quantum[2] = {ldexp(1.0, -sexp[0]), K == 2 ? ldexp(1.0, -sexp[1]) : 0.0};
     for (int64_t item = threadIdx.x; item < ntiles * (8 * K); item += kSmallThreads)
-        weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)));
+        weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)), wm_fix);
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -396,7 +426,7 @@ struct Ring {                       // position in the shared-memory ring
     __device__ __forceinline__ void next() { if (++stage == kStages) { stage = 0; parity ^= 1u; } }
 };
 
-template <int K>
+template <int K, bool DENSE>
 __global__ void __launch_bounds__(kThreads, 1)
 pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 {
@@ -422,6 +452,8 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
     tc_fence_after();
     const uint32_t tmem = pin(*tmem_slot);
     Segment seg;
+    constexpr int kWBytes = DENSE ? kHalves * kWTileBytes : kHalves * kWTileBytes / 2;     // weight tiles per stage
+    constexpr int kStageMmas = DENSE ? kStageGroups : kStageGroups / 2;                    // K = 32 bytes: one group's c and m planes, or two groups' c planes
 
     if (warp == kProducerWarp) {
         // ============ producer warp: per stage two tensor copies (384 samples x 8 groups of words each; rows and
@@ -440,10 +472,10 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                     const uint32_t stage_base = smem_base + ring.stage * kStageBytes, full = bar(kBarFull + ring.stage);
                     const int blk = seg.blk + i;
                     mbar_wait_backoff(bar(kBarEmpty + ring.stage), ring.parity ^ 1u);
-                    mbar_arrive_expect_tx(full, (uint32_t)kStageBytes);
+                    mbar_arrive_expect_tx(full, (uint32_t)(2 * kBoxBytes + kWBytes));
                     tensor_g2s(stage_base, &panel_map, x, blk * kStageGroups, full, pol_stream);
                     tensor_g2s(stage_base + kBoxBytes, &panel_map, x + kBoxSamples / 2, blk * kStageGroups, full, pol_stream);
-                    bulk_g2s(stage_base + 2 * kBoxBytes, p.wt + (int64_t)blk * (kHalves * kWTileBytes), kHalves * kWTileBytes, full, pol_keep);
+                    bulk_g2s(stage_base + 2 * kBoxBytes, p.wt + (int64_t)blk * kWBytes, kWBytes, full, pol_keep);
                 }
             }
         }
@@ -465,7 +497,7 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
                 asm volatile("bar.sync %0, 160;" ::"r"(bar_id) : "memory");    // A buffer written, D drained
                 tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < kStageGroups; q++)      // the first MMA of a segment overwrites D
+                for (int q = 0; q < kStageMmas; q++)        // the first MMA of a segment overwrites D
                     mma_i8_ts(d_tmem, a_tmem + 8 * q, desc + q * (512 >> 4), kWtileDescHi, kIdesc, (i == 0 && q == 0) ? 0u : 1u);
                 mma_commit(bar_aempty);                      // A buffer free once these MMAs have read it
                 mma_commit(bar(kBarEmpty + ring.stage));    // this sub-tile is done with the stage's weight tiles
@@ -520,24 +552,31 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 #pragma unroll
             for (int q = 0; q < kStepGroups; q++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(src + q * kBoxRowBytes));
         };
-        // expand 4 words (64 SNPs) into 32 columns of the A buffer
+        // expand 4 words (64 SNPs) into 32 (c and m planes) or 16 (c planes only) columns of the A buffer
         auto expand_store = [&](const uint32_t (&w)[kStepGroups], int half) {
-            uint32_t r[32];
+            uint32_t r[DENSE ? 32 : 16];
 #pragma unroll
             for (int q = 0; q < kStepGroups; q++) {
-                const uint32_t x = w[q], hb = __umulhi(x, 0x80000000u);        // x >> 1 on the FMA pipe (the ALU pipe is the limit)
+                const uint32_t x = w[q];
+                if (DENSE) {
+                    const uint32_t hb = __umulhi(x, 0x80000000u);              // x >> 1 on the FMA pipe (the ALU pipe is the limit)
 #pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    r[8 * q + s] = x & (0x03030303u << (2 * s));               // c << 2s
-                    // [c == 3] << 2s = x & (x >> 1) & mask in ONE three-input LOP3
-                    asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r[8 * q + 4 + s]) : "r"(x), "r"(hb), "r"(0x01010101u << (2 * s)));
+                    for (int s = 0; s < 4; s++) {
+                        r[8 * q + s] = x & (0x03030303u << (2 * s));           // c << 2s
+                        // [c == 3] << 2s = x & (x >> 1) & mask in ONE three-input LOP3
+                        asm("lop3.b32 %0, %1, %2, %3, 0x80;" : "=r"(r[8 * q + 4 + s]) : "r"(x), "r"(hb), "r"(0x01010101u << (2 * s)));
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) r[4 * q + s] = x & (0x03030303u << (2 * s));
                 }
             }
             if (half == 0) {
                 tc_wait(bar_aempty, aphase ^ 1u);                // the MMAs of the previous stage have read the buffer
                 tc_fence_after();
             }
-            tmem_st32(a_tmem + 32 * half, r);
+            if constexpr (DENSE) tmem_st32(a_tmem + 32 * half, r);
+            else tmem_st16(a_tmem + 16 * half, r);
         };
 
         Ring ring;
@@ -581,7 +620,9 @@ pheno_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap panel_map)
 template <int K>
 __global__ void __launch_bounds__(256)
 tc_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int slots, const TcScale *__restrict__ scale,
-                 double *__restrict__ y1, double *__restrict__ y2, int accumulate)
+                 double *__restrict__ y1, double *__restrict__ y2, int accumulate,
+                 const unsigned long long *__restrict__ corr /* [K][corr_stride] missing-genotype sums in quanta, or NULL */,
+                 int64_t corr_stride)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -590,6 +631,9 @@ tc_reduce_kernel(const double *__restrict__ ypart, int64_t npad, int64_t n, int 
         double s = 0.0;
         for (int q = 0; q < slots; q++) s += ypart[((int64_t)q * K + k) * npad + i];
         s += scale[k].constant;
+        if (corr) {
+            s += ldexp((double)(long long)corr[k * corr_stride + i], scale[k].exponent);
+        }
         if (accumulate) s += (k == 0) ? y1[i] : y2[i];
         if (k == 0) y1[i] = s; else y2[i] = s;
     }
@@ -633,6 +677,22 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     const int slots = (int)((grid + tiles - 1) / tiles) + 1;
     const int64_t npad = tiles * kTile;
 
+    // the m plane as a list of the missing entries (miss_index.cu) when the panel's index is available
+    const int sparse = miss_index_ensure(ctx);
+    if (sparse < 0) return -sparse;
+    long long *wm_fix = nullptr;
+    unsigned long long *corr = nullptr;
+    const int64_t corr_stride = sparse ? miss_corr_stride(ctx) : 0;
+    if (sparse) {
+        wm_fix = (long long *)ctx_scratch(ctx, SCR_WMFIX, (size_t)mc * K * sizeof(long long));
+        const size_t corr_bytes = (size_t)K * corr_stride * sizeof(unsigned long long);
+        corr = (unsigned long long *)ctx_scratch(ctx, SCR_CORR, corr_bytes);
+        if (!wm_fix || !corr) return SIMU_B200_ENOMEM;
+        // one warp per sample stores that sample's sum; only when a sample has more missing genotypes than one warp
+        // takes do several warps add into a zeroed buffer
+        if (miss_correct_accumulates(ctx)) CUDA_TRY(ctx, cudaMemsetAsync(corr, 0, corr_bytes, ctx->stream));
+    }
+
     // weight tiles, then: [TcScale x 2][ticket + pad][partials 4 x kPrepBlocks doubles]
     const size_t wt_bytes = (size_t)nblocks * kHalves * kWTileBytes;
     const size_t aux_off = (wt_bytes + 255) & ~(size_t)255;
@@ -644,8 +704,10 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     unsigned int *ticket = reinterpret_cast<unsigned int *>(wt + aux_off + 32);
     double *partial = reinterpret_cast<double *>(wt + aux_off + 64);
     if (!ctx->tc_attr_set) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         ctx->tc_attr_set = true;
     }
     CUtensorMap map;
@@ -654,12 +716,12 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     CUDA_TRY(ctx, cudaMemsetAsync(ypart, 0, ypart_bytes, ctx->stream));
     int ps = prof_begin(ctx, PROF_LUT_BUILD);
     if (mc <= kSmallMc) {
-        tc_small_prepare_kernel<K><<<1, kSmallThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt);
+        tc_small_prepare_kernel<K><<<1, kSmallThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt, wm_fix);
     } else {
         CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
         tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);
         const int64_t items = nblocks * kHalves * 8 * K;
-        tc_weights_kernel<K><<<(unsigned)((items + 127) / 128), 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt);
+        tc_weights_kernel<K><<<(unsigned)((items + 127) / 128), 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt, wm_fix);
         ctx->launches++;
     }
     prof_end(ctx, ps);
@@ -667,11 +729,22 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     TcParams p;
     p.panel = ctx->panel; p.s16_stride = ctx->s16_stride; p.mc = mc; p.n_samples = n; p.wt = wt; p.scale = scale;
     p.ypart = ypart; p.npad = npad; p.tiles = tiles; p.nblocks = nblocks; p.steps = steps;
+    // The pass over the missing entries (L2-bound gathers, 40 MB of DRAM traffic on config 2) runs on the side stream
+    // BESIDE the main kernel (HBM-bound, one CTA per SM with room for a 256-thread CTA next to it): fork after the weights,
+    // join before the reduce.  Launched after the main kernel so that its CTAs fill the gaps instead of the SMs.
+    if (sparse) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     ps = prof_begin(ctx, PROF_LUT_MAIN);
-    pheno_tc_kernel<K><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p, map);
+    if (sparse) pheno_tc_kernel<K, false><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p, map);
+    else pheno_tc_kernel<K, true><<<(unsigned)grid, kThreads, kSmemBytes, ctx->stream>>>(p, map);
     prof_end(ctx, ps);
+    if (sparse) {
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
+        if ((rc = launch_miss_correct(ctx, ctx->copy_stream, mc, K, wm_fix, corr))) return rc;
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
     ps = prof_begin(ctx, PROF_LUT_REDUCE);
-    tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2, accumulate);
+    tc_reduce_kernel<K><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ypart, npad, n, slots, scale, d_y1, d_y2, accumulate, corr, corr_stride);
     prof_end(ctx, ps);
     ctx->launches += 3;
     return ctx_cuda(ctx, cudaGetLastError(), "pheno_tc launch");

@@ -195,6 +195,7 @@ int launch_repitch(simu_b200_ctx *ctx, const uint8_t *d_src, int64_t src_pitch, 
                    cudaStream_t stream)
 {
     if (n_rows <= 0) return SIMU_B200_OK;
+    miss_index_invalidate(ctx);                   // the panel changes
     if (ctx->layout == SIMU_B200_LAYOUT_SAMPLE16) {
         const int64_t groups = ((dst_row + n_rows - 1) >> 4) - (dst_row >> 4) + 1;
         interleave16_kernel<<<grid_for(ctx, groups * (ctx->s16_stride >> 4)), 256, 0, stream>>>(

@@ -92,3 +92,65 @@ def test_tensor_kernel_zero_effects_and_is_deterministic():
         b1, b2 = ctx.find_pheno(freq, x1, -x1, mode=capi.MODE_FAST)
     assert np.array_equal(a1, b1) and np.array_equal(a2, b2)      # integer sums + fixed slot order: same bits every run
     assert np.array_equal(a2, -a1)                                 # sign symmetry of the fixed-point weights
+
+
+def test_sparse_missing_index_and_dense_plane_are_bit_identical():
+    """The missing genotypes as a list (csrc/miss_index.cu: one correction pass of exact 64-bit integer sums) and as the
+    dense m plane of the MMA must give the SAME BITS: both are the exact sum of the same quantised weights.  Also
+    checks which form runs: the list below 0.4 % missing, the plane above, and again the list after the panel is
+    rewritten with other rows (the index follows the panel)."""
+    import os
+    n, mc = 5003, 3000
+    rows = oracle.synth_rows(20240901, 21, mc, n)                  # 0.1 % missing
+    codes = np.stack([oracle.unpack(rows[j], n) for j in range(mc)])
+    codes[:2500, 17] = 3                                           # one bad sample: more entries than one warp of the pass takes
+    rows = np.stack([oracle.pack(codes[j]) for j in range(mc)])
+    rng = np.random.default_rng(21)
+    x1, x2 = rng.standard_normal(mc), rng.standard_normal(mc)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+        ctx.panel_put_rows(0, rows)
+        _, freq = ctx.find_freq()
+        assert ctx.missing_index()[0] == 0
+        first1, first2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)          # first use of a panel: dense plane, no index yet
+        assert ctx.missing_index()[0] == 0
+        s1, s2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)                  # second use: the index is built
+        assert np.array_equal(first1, s1) and np.array_equal(first2, s2)
+        state, entries = ctx.missing_index()
+        assert state == 1 and entries == int((codes == 3).sum())
+        t1, _ = ctx.find_pheno(freq, x1, None, mode=capi.MODE_FAST)                   # one trait through the same index
+        u1, u2 = ctx.find_pheno(freq[:1000], x1[:1000], x2[:1000], mode=capi.MODE_FAST)   # a prefix of the panel: later rows' entries are skipped
+    os.environ["SIMU_B200_TC_DENSE"] = "1"
+    try:
+        with capi.Context(n) as ctx:
+            ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+            ctx.panel_put_rows(0, rows)
+            d1, d2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+            assert ctx.missing_index()[0] == 2
+            e1, _ = ctx.find_pheno(freq, x1, None, mode=capi.MODE_FAST)
+            v1, v2 = ctx.find_pheno(freq[:1000], x1[:1000], x2[:1000], mode=capi.MODE_FAST)
+    finally:
+        del os.environ["SIMU_B200_TC_DENSE"]
+    assert np.array_equal(s1, d1) and np.array_equal(s2, d2) and np.array_equal(t1, e1)
+    assert np.array_equal(u1, v1) and np.array_equal(u2, v2)
+    o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2, threads=8)
+    assert np.max(np.abs(s1 - o1)) <= 1e-9 * np.max(np.abs(o1)) and np.max(np.abs(s2 - o2)) <= 1e-9 * np.max(np.abs(o2))
+    # above the rate limit the plane is used; rewriting the panel rebuilds the index
+    dense_rows = rows.copy()
+    codes[rng.random((mc, n)) < 0.02] = 3
+    dense_rows = np.stack([oracle.pack(codes[j]) for j in range(mc)])
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+        ctx.panel_put_rows(0, dense_rows)
+        _, f2 = ctx.find_freq()
+        h1, h2 = ctx.find_pheno(f2, x1, x2, mode=capi.MODE_FAST)
+        h1, h2 = ctx.find_pheno(f2, x1, x2, mode=capi.MODE_FAST)
+        assert ctx.missing_index()[0] == 2
+        p1, p2 = oracle.find_pheno(dense_rows, n, f2, x1, x2, threads=8)
+        assert np.max(np.abs(h1 - p1)) <= 1e-9 * np.max(np.abs(p1)) and np.max(np.abs(h2 - p2)) <= 1e-9 * np.max(np.abs(p2))
+        ctx.panel_put_rows(0, rows)                                # back to the sparse panel: the index is rebuilt
+        assert ctx.missing_index()[0] == 0
+        r1, r2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+        r1, r2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+        assert ctx.missing_index()[0] == 1
+        assert np.array_equal(r1, s1) and np.array_equal(r2, s2)
