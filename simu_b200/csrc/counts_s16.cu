@@ -22,6 +22,8 @@
 //
 // One warp per 16-row group; 2/4/8 warps of a CTA share a group (sample ranges) when there are fewer
 // groups than resident warps.  Algorithmic bytes: ceil(N/4) + 24 per SNP.
+#include <stdlib.h>
+
 #include "ctx.cuh"
 
 namespace {
@@ -202,13 +204,235 @@ counts_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int64_t
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Second form: the words arrive through a shared-memory ring filled by TMA bulk copies.
+//
+// The kernel above keeps 8 x 16 bytes per lane in flight in REGISTERS; at 128 registers per thread that is 16 warps and
+// 64 KB per SM, and the warps alternate between waiting for their loads and folding them (ncu: long-scoreboard-bound,
+// 0.89-0.94 of the HBM roofline on config 2).  Here every warp owns a ring of kRing 8 KB slots: one lane issues
+// cp.async.bulk copies two slots ahead, the warp folds a slot out of shared memory (conflict-free LDS.128) and refills
+// it -- 128 KB in flight per SM whatever the register allocation, and no producer warp or cross-warp barrier.
+//
+// Work split: the (group, 8 KB chunk) list in group-major order is cut into one CONTIGUOUS range per warp, equal to
+// within one chunk.  A warp that covers a whole group writes its counts directly; groups that straddle ranges are
+// combined through global atomics and a ticket per group, and the last piece to arrive finalises (and zeroes the
+// accumulators again for the next call).
+constexpr int kRing = 3;
+constexpr int kSlotBytes = 8192;                  // 512 vectors = 2048 samples of one group
+constexpr int kSlotVecs = kSlotBytes / 16;
+constexpr int kWarpsT = 8;
+constexpr int kSmemT = kWarpsT * kRing * kSlotBytes + kWarpsT * kRing * 8;
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// two rounds (16 vectors per lane) of one slot -> two weight-32 words per tree; vectors >= nv read as zero
+template <int NLEV>
+__device__ __forceinline__ void slot_rounds(uint32_t slot, int lane, int nv, Sliced<NLEV> &R, Sliced<NLEV> &A, uint32_t (&r32)[2], uint32_t (&a32)[2])
+{
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t w[32], b[32];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int v = (8 * h + q) * 32 + lane;
+            uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
+            if (v < nv) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(slot + 16u * (uint32_t)v));
+            w[4 * q] = x0; w[4 * q + 1] = x1; w[4 * q + 2] = x2; w[4 * q + 3] = x3;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; q++) b[q] = w[q] & (w[q] * 2u);
+        r32[h] = R.template fold<0, 5, 0>(w);
+        a32[h] = A.template fold<0, 5, 0>(b);
+    }
+}
+
+struct S16Tma {
+    const uint8_t *panel;
+    int64_t s16_stride, mc, n_samples;
+    int32_t *counts;
+    double *freq;
+    unsigned int *acc;          // [groups][48] partial sums + [groups] tickets after them; all zero between calls
+    int64_t ngroups;
+    int cpg;                    // chunks per group
+    int64_t total;              // ngroups * cpg
+};
+
+__device__ __forceinline__ int64_t warp_of_chunk(int64_t x, int64_t warps, int64_t total) { return ((x + 1) * warps - 1) / total; }
+
+template <int NLEV>
+__global__ void __launch_bounds__(kWarpsT * 32, 1)
+counts_s16_tma_kernel(const S16Tma p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // participating warps: never more than chunks, so that no range is empty (the ticket of a straddling group counts
+    // the warps between its first and its last owner)
+    const int64_t launched = (int64_t)gridDim.x * kWarpsT, warps = launched < p.total ? launched : p.total;
+    const int64_t me = (int64_t)blockIdx.x * kWarpsT + warp;
+    const int64_t c_begin = me < warps ? (me * p.total) / warps : 0, c_end = me < warps ? ((me + 1) * p.total) / warps : 0;
+    const uint32_t ring = smem_addr(smem) + (uint32_t)(warp * kRing * kSlotBytes);
+    const uint32_t bars = smem_addr(smem) + (uint32_t)(kWarpsT * kRing * kSlotBytes + warp * kRing * 8);
+    if (lane == 0) {
+        for (int s = 0; s < kRing; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8u * s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (c_begin >= c_end) return;
+    const int64_t row_bytes = p.s16_stride;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    auto chunk_bytes = [&](int c) { const int64_t left = row_bytes - (int64_t)c * kSlotBytes; return (uint32_t)(left < kSlotBytes ? left : kSlotBytes); };
+    // producer cursor (lane 0 issues): chunk id -> (group, chunk in group)
+    int64_t pid = c_begin;
+    int64_t pg = c_begin / p.cpg;
+    int pc = (int)(c_begin - pg * p.cpg), pslot = 0;
+    auto issue = [&]() {
+        if (pid < c_end) {
+            if (lane == 0) {
+                const uint32_t bytes = chunk_bytes(pc), bar = bars + 8u * pslot;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                             ::"r"(ring + (uint32_t)(pslot * kSlotBytes)), "l"(p.panel + pg * row_bytes + (int64_t)pc * kSlotBytes), "r"(bytes), "r"(bar), "l"(policy)
+                             : "memory");
+            }
+            pid++;
+            if (++pc == p.cpg) { pc = 0; pg++; }
+            if (++pslot == kRing) pslot = 0;
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < kRing; s++) issue();
+
+    int nlev = 1;
+    while (nlev < NLEV && (p.n_samples >> nlev) != 0) nlev++;          // counts <= N < 2^nlev
+    int64_t g = c_begin / p.cpg;
+    int c = (int)(c_begin - g * p.cpg), slot = 0;
+    uint32_t phase = 0;
+    int64_t id = c_begin;
+    while (id < c_end) {
+        // one piece: the chunks [c, c_last] of group g that lie in this warp's range
+        const int c_stop = (int)min((int64_t)p.cpg, (int64_t)c + (c_end - id));       // exclusive
+        Sliced<NLEV> R, A;
+        R.clear(); A.clear();
+        auto wait_slot = [&]() {
+            const uint32_t bar = bars + 8u * slot;
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+        };
+        auto next_slot = [&]() {
+            __syncwarp();                       // every lane has its words in registers: the slot may be overwritten
+            issue();
+            if (++slot == kRing) { slot = 0; phase ^= 1u; }
+            id++; c++;
+        };
+        // One slot per iteration, NOT unrolled: the two rounds' weight-32 words meet in one carry-save adder at level 5
+        // and the carry is ripple-added from level 6 up (0.7 ALU instructions per word more than folding 8 rounds
+        // through levels 5-7 first, which unrolled to 40 KB of code: with 8 warps per SM the instruction fetch then
+        // showed as the top stall, `no_instruction` 2.5 per issue).
+#pragma unroll 1
+        while (c < c_stop) {
+            uint32_t r2[2], a2[2], cr, ca;
+            const int nv = (int)(chunk_bytes(c) >> 4);
+            wait_slot();
+            slot_rounds<NLEV>(ring + (uint32_t)(slot * kSlotBytes), lane, nv, R, A, r2, a2);
+            next_slot();
+            csa(R.lvl[5], cr, R.lvl[5], r2[0], r2[1]);
+            csa(A.lvl[5], ca, A.lvl[5], a2[0], a2[1]);
+            R.template ripple<6>(cr, nlev);
+            A.template ripple<6>(ca, nlev);
+        }
+        // the piece's counts: lanes' counters added, lane p extracts bit position p
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { R.add_lane(off, nlev); A.add_lane(off, nlev); }
+        const uint32_t mine = R.extract(lane, nlev);            // even lane 2f: low-bit count, odd 2f+1: high-bit count
+        uint32_t both = A.extract(lane, nlev);                  // odd lane 2f+1: both-bits count
+        uint32_t lo = __shfl_sync(0xffffffffu, mine, lane & ~1), hi = mine;        // valid on odd lanes
+        // pieces of this group = warps whose ranges touch it
+        const int64_t first_w = warp_of_chunk(g * p.cpg, warps, p.total), last_w = warp_of_chunk((g + 1) * p.cpg - 1, warps, p.total);
+        bool finalise = true;
+        if (first_w != last_w) {
+            unsigned int *acc = p.acc + g * 48, *ticket = p.acc + p.ngroups * 48 + g;
+            if (lane & 1) {
+                atomicAdd(acc + 3 * (lane >> 1), lo);
+                atomicAdd(acc + 3 * (lane >> 1) + 1, hi);
+                atomicAdd(acc + 3 * (lane >> 1) + 2, both);
+            }
+            __threadfence();
+            __syncwarp();
+            unsigned int t = 0;
+            if (lane == 0) t = atomicAdd(ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            finalise = t == (unsigned int)(last_w - first_w);
+            if (finalise) {
+                __threadfence();
+                if (lane & 1) {
+                    lo = atomicExch(acc + 3 * (lane >> 1), 0u);
+                    hi = atomicExch(acc + 3 * (lane >> 1) + 1, 0u);
+                    both = atomicExch(acc + 3 * (lane >> 1) + 2, 0u);
+                }
+                if (lane == 0) *ticket = 0u;
+            }
+        }
+        if (finalise && (lane & 1)) {
+            const int64_t j = 16 * g + (lane >> 1);
+            if (j < p.mc) {
+                const int n3 = (int)both, n1 = (int)(lo - both), n2 = (int)(hi - both);
+                const int n0 = (int)p.n_samples - n1 - n2 - n3;
+                if (p.counts) reinterpret_cast<int4 *>(p.counts)[j] = make_int4(n0, n1, n2, n3);
+                if (p.freq) {
+                    const int nm = n2 + n1 + n0;               // source.cc:874
+                    p.freq[j] = (nm == 0) ? 0.0                // source.cc:875
+                                          : static_cast<double>(2 * n0 + 1 * n1) / static_cast<double>(2 * nm);
+                }
+            }
+        }
+        if (c == p.cpg) { c = 0; g++; }
+    }
+}
+
 }  // namespace
+
+static int launch_counts_s16_tma(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int32_t *d_counts, double *d_freq)
+{
+    S16Tma p;
+    p.panel = ctx->panel; p.s16_stride = ctx->s16_stride; p.mc = mc; p.n_samples = ctx->n_samples; p.counts = d_counts; p.freq = d_freq;
+    p.ngroups = (mc + 15) >> 4;
+    p.cpg = (int)((ctx->s16_stride + kSlotBytes - 1) / kSlotBytes);
+    p.total = p.ngroups * p.cpg;
+    // partial sums of the groups that straddle two warps' ranges + their tickets: zero between calls (the finalising
+    // warp clears what it reads), so only a new or larger buffer is cleared here
+    const size_t acc_bytes = (size_t)p.ngroups * 49 * sizeof(unsigned int);
+    const bool fresh = ctx->scratch_bytes[SCR_CNTACC] < acc_bytes;
+    p.acc = (unsigned int *)ctx_scratch(ctx, SCR_CNTACC, acc_bytes);
+    if (!p.acc) return SIMU_B200_ENOMEM;
+    if (fresh) CUDA_TRY(ctx, cudaMemsetAsync(p.acc, 0, ctx->scratch_bytes[SCR_CNTACC], stream));
+    if (!ctx->cnt_attr_set) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(counts_s16_tma_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemT));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(counts_s16_tma_kernel<kMaxLevels>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemT));
+        ctx->cnt_attr_set = true;
+    }
+    int64_t blocks = (p.total + kWarpsT - 1) / kWarpsT;
+    if (blocks > ctx->num_sms) blocks = ctx->num_sms;
+    if (ctx->n_samples < (1 << 20)) counts_s16_tma_kernel<20><<<(unsigned)blocks, kWarpsT * 32, kSmemT, stream>>>(p);
+    else counts_s16_tma_kernel<kMaxLevels><<<(unsigned)blocks, kWarpsT * 32, kSmemT, stream>>>(p);
+    ctx->launches++;
+    return ctx_cuda(ctx, cudaGetLastError(), "counts_s16_tma_kernel launch");
+}
 
 int launch_counts_s16(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int32_t *d_counts, double *d_freq)
 {
     if (mc <= 0) return SIMU_B200_OK;
     const int64_t groups = (mc + 15) >> 4;
     const int64_t max_blocks = (int64_t)ctx->num_sms * 2;            // 2 CTAs of 8 warps per SM
+    // Which kernel: with at least 8 whole groups per resident warp the register-fed kernel needs no sample split and
+    // no cross-warp combine and is the faster one (config 4: 4.95 against 5.12 ms); below that the TMA-fed ring with
+    // its balanced contiguous ranges wins (config 2: 0.375 against 0.428 ms, config 3: 0.055 against 0.067 ms).
+    // SIMU_B200_COUNTS=reg|tma forces one of them (A/B runs).
+    const char *force = getenv("SIMU_B200_COUNTS");
+    const bool tma = force ? force[0] == 't' : groups < 8 * max_blocks * kWarps;
+    if (tma) return launch_counts_s16_tma(ctx, stream, mc, d_counts, d_freq);
     const int64_t resident = max_blocks * kWarps;
     // static grid-stride assignment: aim at >= 8 (group, sample range) tasks per resident warp so that the last,
     // partly filled round costs a few per cent, not a third (6250 groups on 2368 warps: 2.6 rounds)

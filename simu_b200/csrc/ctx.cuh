@@ -53,7 +53,7 @@ struct simu_b200_ctx {
     bool prof_alloc = false;
 
     bool lut_attr_set[3] = {false, false, false};
-    bool tc_attr_set = false;
+    bool tc_attr_set = false, cnt_attr_set = false;
     int coop_sort_blocks = -1;           // co-resident blocks of the cooperative sort (-1: not queried)
     int64_t launches = 0;
     float last_ms[2] = {0.f, 0.f};
@@ -72,7 +72,7 @@ struct simu_b200_ctx {
 enum ScratchSlot {
     SCR_ROWS = 0, SCR_COUNTS, SCR_FREQ, SCR_X1, SCR_X2, SCR_Y1, SCR_Y2, SCR_NOISE,
     SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG, SCR_TCW,
-    SCR_MISS_CNT, SCR_MISS_ENT, SCR_MISS_OFF, SCR_WMFIX, SCR_CORR
+    SCR_MISS_CNT, SCR_MISS_ENT, SCR_MISS_OFF, SCR_WMFIX, SCR_CORR, SCR_CNTACC
 };
 
 int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...);

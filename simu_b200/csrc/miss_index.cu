@@ -137,6 +137,8 @@ int miss_index_ensure(simu_b200_ctx *ctx)
     // runs dense, the index is built when the same panel is used again (several simulations over one resident panel;
     // a drop-in run that stages, simulates once and exits never pays for it).  Both forms give the same bits.
     if (++ctx->miss_uses < 2) return 0;
+    // small panels are launch-bound (config 1: 7 launches of a few microseconds): one more kernel costs more than the plane
+    if ((double)ctx->panel_rows * (double)ctx->n_samples < 2.5e8 && !getenv("SIMU_B200_TC_SPARSE")) { ctx->miss_state = 2; return 0; }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(ctx->stream, &cap);
     if (cap != cudaStreamCaptureStatusNone) return 0;                      // the build synchronises: not inside a capture

@@ -326,6 +326,28 @@ def test_group4_counts_warp_split_paths(n, mc):
     assert np.array_equal(counts, oc) and np.array_equal(freq, of)
 
 
+@pytest.mark.parametrize("which", ["tma", "reg"])
+@pytest.mark.parametrize("n,mc", [(100_000, 9), (100_000, 700), (40_000, 5000), (5, 4000), (1, 1), (2049, 33), (8193, 17), (33_333, 257),
+                                  (600, 40_000)])
+def test_sample16_counts_both_kernels(which, n, mc, monkeypatch):
+    """counts_s16_tma_kernel (shared-memory ring, contiguous chunk ranges: whole groups per warp, groups that straddle
+    two or more warps' ranges, more warps than chunks) and counts_s16_kernel (register-fed, 1/2/4/8 warps per group)
+    -- the library picks by shape, SIMU_B200_COUNTS forces -- both bit-exact, twice in a row (the straddling groups'
+    accumulators must be left at zero)."""
+    monkeypatch.setenv("SIMU_B200_COUNTS", which)
+    with capi.Context(n) as ctx:
+        ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+        ctx.panel_synth(PANEL_SEED, 13, mc)
+        counts, freq = ctx.find_freq()
+        counts2, freq2 = ctx.find_freq()
+        part, _ = ctx.find_freq(mc=max(1, mc // 3))                 # a prefix of the panel
+        rows = ctx.panel_get_rows(0, mc)
+    oc, of = oracle.find_freq_threaded(rows, n, 8)
+    assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+    assert np.array_equal(counts2, oc) and np.array_equal(freq2, of)
+    assert np.array_equal(part, oc[:max(1, mc // 3)])
+
+
 # ---------------------------------------------------------------- kernel (c)
 
 def test_apply_heritability_parity():

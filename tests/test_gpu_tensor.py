@@ -100,6 +100,7 @@ def test_sparse_missing_index_and_dense_plane_are_bit_identical():
     checks which form runs: the list below 0.4 % missing, the plane above, and again the list after the panel is
     rewritten with other rows (the index follows the panel)."""
     import os
+    os.environ["SIMU_B200_TC_SPARSE"] = "1"                        # small panels default to the dense plane (launch-bound)
     n, mc = 5003, 3000
     rows = oracle.synth_rows(20240901, 21, mc, n)                  # 0.1 % missing
     codes = np.stack([oracle.unpack(rows[j], n) for j in range(mc)])
@@ -154,3 +155,4 @@ def test_sparse_missing_index_and_dense_plane_are_bit_identical():
         r1, r2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
         assert ctx.missing_index()[0] == 1
         assert np.array_equal(r1, s1) and np.array_equal(r2, s2)
+    del os.environ["SIMU_B200_TC_SPARSE"]
