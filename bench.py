@@ -427,7 +427,10 @@ class Workload:
         _, bytes_counts, bytes_pheno = alg_bytes(w)
         peaks, peak_src = _peaks()
         names = KERNEL_NAMES[self.args.layout]
+        if self.args.layout == "s16" and (mc + 15) // 16 < 8 * 2 * torch.cuda.get_device_properties(self.dev).multi_processor_count * 8:
+            names = ("counts_s16_tma_kernel",) + names[1:]      # the library's own choice by shape (counts_s16.cu)
         fast = self.mode == self.capi.MODE_FAST
+        miss_state, miss_entries = ctx.missing_index() if self.args.layout == "s16" else (0, 0)
         main_ms, main_n = prof["pheno_fast" if fast else "pheno_exact"]
         cnt_ms, cnt_n = prof["counts"]
         out = {
@@ -441,6 +444,9 @@ class Workload:
             "kernel_ms": {kname: (v[0] / v[1] if v[1] else None) for kname, v in prof.items()},
             "clocks": sampler.summary(t_wall0, t_wall1) if sampler else None,
             "checksum_device": float(self.d_y.abs().sum().item()),
+            # find_pheno FAST on SAMPLE16 panels: the missing genotypes as a sparse list built once per panel (at its second
+            # use) with the correction pass beside the main kernel, or as a dense plane of the MMA (include/simu_b200.h)
+            "missing_genotypes": {1: f"sparse index, {miss_entries} entries", 2: "dense MMA plane", 0: "dense MMA plane (index not built)"}[miss_state],
         }
         return out
 
@@ -608,7 +614,7 @@ def run_ours(args, w):
             also[name] = {"desc": ow["desc"], "n_samples": ow["n"], "n_causal_per_gpu": ow["mc"], "traits": ow["k"],
                           "parallelism": f"snp-shard x{world}, 1 all-reduce ({o.allreduce})" if world > 1 else "single GPU",
                           **{kk: r[kk] for kk in ("value", "ms_per_step", "steps", "cuda_graph", "gpu_launches_per_step", "bed_gbs",
-                                                  "roofline", "roofline_counts", "kernel_ms", "clocks")}}
+                                                  "roofline", "roofline_counts", "kernel_ms", "clocks", "missing_genotypes")}}
             o.close()
 
     if rank == 0:
@@ -627,7 +633,7 @@ def run_ours(args, w):
                        "n_causal_per_gpu": mc, "traits": k, "mode": args.mode, "hbm_panel": panel_desc,
                        "step": "find_freq -> effect scaling on the device -> find_pheno -> apply_heritability per trait" if wl.one_call
                                else "find_freq -> find_pheno -> apply_heritability per trait" + (" -> liability split" if w["cc"] else ""),
-                       "cuda_graph": res["cuda_graph"],
+                       "cuda_graph": res["cuda_graph"], "missing_genotypes": res["missing_genotypes"],
                        "l2": f"inputs larger than L2 ({mc * B / 1e6:.0f} MB of causal rows per pass, 126 MB L2)",
                        "parallelism": f"snp-shard x{world}, 1 all-reduce ({wl.allreduce})" if world > 1 else "single GPU"},
             "bed_gbs": res["bed_gbs"],

@@ -318,8 +318,8 @@ SIMU_B200_API void simu_b200_peer_close(simu_b200_ctx *ctx);
  * the panel; it depends on the panel only, like the layout), the first call runs with the dense plane of the MMA;
  * from then on each call adds the entries' weights as exact 64-bit integers beside the main kernel.  *state: 0 = not
  * built (fewer than two FAST calls since the panel changed), 1 = sparse list in use (*entries = its length), 2 =
- * dense plane in use (more than 0.4 % missing genotypes, or SIMU_B200_TC_DENSE set).  Both forms give bit-identical
- * results. */
+ * dense plane in use (more than 0.4 % missing genotypes, a panel of fewer than 2.5e8 genotypes, or SIMU_B200_TC_DENSE set).  Both forms
+ * are the exact sum of the same quantised weights and agree to FP64 rounding (~1e-16 of max|y|). */
 SIMU_B200_API int simu_b200_missing_index(const simu_b200_ctx *ctx, int *state, int64_t *entries);
 
 /* Device time in milliseconds of the last find_freq / find_pheno call on this

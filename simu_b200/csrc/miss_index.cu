@@ -8,7 +8,9 @@
 // entries are missing depends on the panel only, not on effects or frequencies.  Each call then adds
 //     corr_i = sum over sample i's missing entries j of round(Wm_j / quantum)          (64-bit integers)
 // in a separate pass over the list (1.6 % of the panel's bytes at a 0.1 % missing rate).  Integer sums are exact
-// and order-independent, so the result is the same exact fixed-point sum the dense plane produced, bit for bit.
+// and order-independent, so the result is the same exact fixed-point sum the dense plane produces; the two forms
+// differ only in where integers become FP64 (per drained segment there, once per sample here): equal to FP64
+// rounding, ~1e-16 of max|y|.
 //
 // Layout: compressed rows BY SAMPLE: offsets[i] .. offsets[i + 1] delimit sample i's entries, an entry is the
 // panel row of a missing genotype (4 bytes, in no particular order).  The correction pass gives every sample a

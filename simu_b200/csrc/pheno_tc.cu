@@ -39,7 +39,7 @@
 // (miss_index.cu: a list of the missing entries built once per panel) the kernel runs WITHOUT the m plane --
 // K = 32 bytes then cover the c planes of two groups, half the tensor-memory traffic and half the MMAs -- and
 // miss_correct_kernel adds sum_j Wm_j m_ij from the list as exact 64-bit integers in the same quantum: the same
-// fixed-point sum, bit for bit (config 2: 0.547 -> 0.375 ms + 0.03 ms).  DENSE = true keeps the plane (index not
+// fixed-point sum, equal to FP64 rounding (config 2: 0.547 -> 0.375 ms, the list pass runs beside it).  DENSE = true keeps the plane (index not
 // applicable or more than 0.4 % missing).
 //
 // Algorithmic bytes: Mc (ceil(N/4) + 12 + 8K) + 8NK.

@@ -66,6 +66,14 @@ def _full(n, m, mc, k2, seed, gcta=False):
         _tol(f1, o1)
         if k2:
             _tol(f2, o2)
+        # the second FAST call on a panel runs with the sparse missing-genotype index instead of the dense MMA plane
+        # (csrc/miss_index.cu; panels of >= 2.5e8 genotypes): the same exact fixed-point sums, converted to FP64 in
+        # another order -> equal to FP64 rounding
+        g1, g2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
+        assert ctx.missing_index()[0] == (1 if n * mc >= 2.5e8 else 2)
+        _tol(g1, f1, 1e-13)
+        if k2:
+            _tol(g2, f2, 1e-13)
 
 
 def test_config1_full():      # 10K x 100K, --causal-n 1000, one trait
@@ -110,6 +118,11 @@ def _column_block(n, m, mc, k2, seed, s0, ns=2048, count_rows=512):
         if k2:
             _tol(f2, e2)
             _tol(f2[s0:s0 + ns], o2)
+        g1, g2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)      # second use of the panel: sparse missing-genotype index
+        assert ctx.missing_index()[0] == 1 and ctx.missing_index()[1] == int(counts[:, 3].sum())
+        _tol(g1, f1, 1e-13)                                              # same fixed-point sums, another FP64 conversion order
+        if k2:
+            _tol(g2, f2, 1e-13)
         assert abs(e1.sum()) <= 1e-9 * np.abs(e1).sum()        # centring identity over ALL samples
 
 

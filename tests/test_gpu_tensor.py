@@ -94,9 +94,10 @@ def test_tensor_kernel_zero_effects_and_is_deterministic():
     assert np.array_equal(a2, -a1)                                 # sign symmetry of the fixed-point weights
 
 
-def test_sparse_missing_index_and_dense_plane_are_bit_identical():
+def test_sparse_missing_index_and_dense_plane_agree():
     """The missing genotypes as a list (csrc/miss_index.cu: one correction pass of exact 64-bit integer sums) and as the
-    dense m plane of the MMA must give the SAME BITS: both are the exact sum of the same quantised weights.  Also
+    dense m plane of the MMA are the exact sum of the same quantised weights; only the points where integers become
+    FP64 differ, so the results agree to FP64 rounding (1e-13 of max|y| stated; identical bits on this small case).  Also
     checks which form runs: the list below 0.4 % missing, the plane above, and again the list after the panel is
     rewritten with other rows (the index follows the panel)."""
     import os
@@ -116,7 +117,7 @@ def test_sparse_missing_index_and_dense_plane_are_bit_identical():
         first1, first2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)          # first use of a panel: dense plane, no index yet
         assert ctx.missing_index()[0] == 0
         s1, s2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)                  # second use: the index is built
-        assert np.array_equal(first1, s1) and np.array_equal(first2, s2)
+        assert np.max(np.abs(first1 - s1)) <= 1e-13 * np.max(np.abs(s1)) and np.max(np.abs(first2 - s2)) <= 1e-13 * np.max(np.abs(s2))
         state, entries = ctx.missing_index()
         assert state == 1 and entries == int((codes == 3).sum())
         t1, _ = ctx.find_pheno(freq, x1, None, mode=capi.MODE_FAST)                   # one trait through the same index
@@ -132,8 +133,8 @@ def test_sparse_missing_index_and_dense_plane_are_bit_identical():
             v1, v2 = ctx.find_pheno(freq[:1000], x1[:1000], x2[:1000], mode=capi.MODE_FAST)
     finally:
         del os.environ["SIMU_B200_TC_DENSE"]
-    assert np.array_equal(s1, d1) and np.array_equal(s2, d2) and np.array_equal(t1, e1)
-    assert np.array_equal(u1, v1) and np.array_equal(u2, v2)
+    for a, b in ((s1, d1), (s2, d2), (t1, e1), (u1, v1), (u2, v2)):
+        assert np.max(np.abs(a - b)) <= 1e-13 * np.max(np.abs(b))
     o1, o2 = oracle.find_pheno(rows, n, freq, x1, x2, threads=8)
     assert np.max(np.abs(s1 - o1)) <= 1e-9 * np.max(np.abs(o1)) and np.max(np.abs(s2 - o2)) <= 1e-9 * np.max(np.abs(o2))
     # above the rate limit the plane is used; rewriting the panel rebuilds the index
@@ -154,5 +155,5 @@ def test_sparse_missing_index_and_dense_plane_are_bit_identical():
         r1, r2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
         r1, r2 = ctx.find_pheno(freq, x1, x2, mode=capi.MODE_FAST)
         assert ctx.missing_index()[0] == 1
-        assert np.array_equal(r1, s1) and np.array_equal(r2, s2)
+        assert np.array_equal(r1, s1) and np.array_equal(r2, s2)             # the same path twice: the same bits
     del os.environ["SIMU_B200_TC_SPARSE"]
