@@ -355,7 +355,7 @@ class Workload:
 
     def measure(self, steps, warmup, sampler, prof_steps=20):
         """-> dict: value, ms_per_step, kernel_ms, rooflines, clocks, launches.  The timed region replays ONE
-        CUDA graph of the step per iteration when the step could be captured (single GPU; the launch-bound
+        CUDA graph of the step per iteration when the step could be captured (the launch-bound
         sparse configs are 10 launches of microseconds each); per-kernel times for the roofline come from a
         second, eager region with the library's event pairs around every launch."""
         torch, dist, ctx, w = self.torch, self.dist, self.ctx, self.w
@@ -375,7 +375,9 @@ class Workload:
         graph = None
         # (EXACT mode is timed eagerly: its SAMPLE16 kernel takes the effects as kernel parameters fetched from the device at call
         # time, which a stream capture does not allow -- under capture the library falls back to its slower table kernel)
-        if self.world == 1 and self.args.graph != "off" and self.mode == self.capi.MODE_FAST:
+        # N > 1: the exchange over NVLink peer memory is the library's own kernel with its epoch in device memory, so the whole
+        # step -- exchange included -- is one graph on every rank (the NCCL fallback is launched eagerly)
+        if (self.world == 1 or self.allreduce == "peer") and self.args.graph != "off" and self.mode == self.capi.MODE_FAST:
             try:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=self.stream):

@@ -44,6 +44,14 @@ __device__ __forceinline__ void grid_barrier_sys(uint32_t *barrier, uint32_t tar
     __syncthreads();
 }
 
+__device__ __forceinline__ uint32_t ld_state(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 // raise flag `round` of this rank's epoch in every peer's memory, then wait for every peer's
 __device__ __forceinline__ void flag_round(const PeerPtrs &pp, int round, int rank, int world, int parity, uint32_t epoch)
 {
@@ -69,13 +77,20 @@ __device__ __forceinline__ void flag_round(const PeerPtrs &pp, int round, int ra
 constexpr int kPeerThreads = 1024;
 
 __global__ void __launch_bounds__(kPeerThreads)
-peer_allreduce_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t epoch, int64_t count, double *__restrict__ y,
-                      double *__restrict__ mine, uint32_t *barrier, uint32_t barrier_target)
+peer_allreduce_kernel(PeerPtrs pp, int rank, int world, int64_t count, double *__restrict__ y, uint32_t *state)
 {
+    // The epoch lives in DEVICE memory (state[1]; state[0] is the grid-barrier counter, monotonic): a launch derives its
+    // epoch, buffer parity and barrier target from it and advances it after its last grid barrier, when every block
+    // has read it.  Nothing in the launch parameters changes from call to call, so the step that contains the exchange
+    // can be captured into a CUDA graph and replayed.
+    const uint32_t epoch = ld_state(state + 1) + 1u;
+    const int parity = (int)(epoch & 1u);
+    double *mine = const_cast<double *>(pp.buf[rank]) + (int64_t)parity * count;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = first; i < count; i += stride) mine[i] = y[i];
     // grid barrier: every block's part of the partial is written (system scope: the peers will read it)
-    grid_barrier_sys(barrier, barrier_target);
+    grid_barrier_sys(state, epoch * gridDim.x);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st_state(state + 1, epoch);
     flag_round(pp, 0, rank, world, parity, epoch);
     // pairs of doubles (the buffers are 16-byte aligned when count is even), all peers' loads in flight at once;
     // rank order of the adds: the same bits on every rank
@@ -109,13 +124,16 @@ peer_allreduce_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t epo
 // two-shot: publish | barrier | flags A | reduce my slice from all partials | barrier | flags B | gather the slices.
 // count2 = count / 2 pairs of doubles (the host routes odd counts and unaligned y to the one-shot kernel).
 __global__ void __launch_bounds__(kPeerThreads)
-peer_allreduce2_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t epoch, int64_t count, double *__restrict__ y,
-                       double *__restrict__ mine, double *__restrict__ my_slices, uint32_t *barrier, uint32_t barrier_target)
+peer_allreduce2_kernel(PeerPtrs pp, int rank, int world, int64_t count, double *__restrict__ y, uint32_t *state)
 {
+    const uint32_t epoch = ld_state(state + 1) + 1u;             // see peer_allreduce_kernel
+    const int parity = (int)(epoch & 1u);
+    double *mine = const_cast<double *>(pp.buf[rank]) + (int64_t)parity * count;
+    double *my_slices = const_cast<double *>(pp.buf[rank]) + (int64_t)(2 + parity) * count;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t pairs = count / 2;
     for (int64_t i = first; i < pairs; i += stride) reinterpret_cast<double2 *>(mine)[i] = reinterpret_cast<const double2 *>(y)[i];
-    grid_barrier_sys(barrier, barrier_target - gridDim.x);
+    grid_barrier_sys(state, (2u * epoch - 1u) * gridDim.x);
     flag_round(pp, 0, rank, world, parity, epoch);
     // reduce-scatter: pairs [lo, hi) are this rank's; every peer's partial is read for that slice only
     const int64_t lo = pairs * rank / world, hi = pairs * (rank + 1) / world;
@@ -135,7 +153,8 @@ peer_allreduce2_kernel(PeerPtrs pp, int rank, int world, int parity, uint32_t ep
         reinterpret_cast<double2 *>(my_slices)[i] = make_double2(s0, s1);
         reinterpret_cast<double2 *>(y)[i] = make_double2(s0, s1);
     }
-    grid_barrier_sys(barrier, barrier_target);
+    grid_barrier_sys(state, 2u * epoch * gridDim.x);
+    if (blockIdx.x == 0 && threadIdx.x == 0) st_state(state + 1, epoch);
     flag_round(pp, 1, rank, world, parity, epoch);
     // all-gather: the peers' reduced slices, straight into y
     for (int64_t i = first; i < pairs; i += stride) {
@@ -156,10 +175,9 @@ struct simu_b200_peer {
     double *sym = nullptr;             // [2][count] then the flag block
     void *peer_base[kMaxPeers] = {nullptr};
     PeerPtrs pp;
-    uint32_t epoch = 0;
-    uint32_t *barrier = nullptr;       // grid-barrier counter of the all-reduce kernel (monotonic)
-    uint32_t barrier_target = 0;
+    uint32_t *barrier = nullptr;       // device state: [0] grid-barrier counter (monotonic), [1] epoch of the last all-reduce
     bool connected = false;
+    int form = -1;                     // -1 not used yet, 0 one-shot, 1 two-shot
 };
 
 static size_t sym_bytes(int64_t count) { return (size_t)4 * count * sizeof(double) + 4 * kMaxPeers * sizeof(uint32_t); }
@@ -218,25 +236,17 @@ int simu_b200_peer_allreduce_dev(simu_b200_ctx *ctx, double *d_y, int64_t count)
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     simu_b200_peer *p = ctx->peer;
     if (!d_y || count != p->count) return ctx_fail(ctx, SIMU_B200_EINVAL, "peer_allreduce: count differs from peer_init");
-    const uint32_t epoch = ++p->epoch;
-    const int parity = (int)(epoch & 1u);
     int blocks = (int)std::min<int64_t>((count + 2 * kPeerThreads - 1) / (2 * kPeerThreads), (int64_t)ctx->num_sms);   // co-resident
-    double *mine = p->sym + (int64_t)parity * count;
     // more than two ranks: two-shot (reduce-scatter + all-gather), which moves 2 (world-1)/world of the payload per
-    // rank instead of (world-1) x; SIMU_B200_PEER_ONESHOT=1 forces the one-shot form (A/B runs)
+    // rank instead of (world-1) x; SIMU_B200_PEER_ONESHOT=1 forces the one-shot form (A/B runs).  The form must not
+    // change between calls on one context: the grid-barrier counter advances by one or two rounds per epoch.
     const bool two_shot = p->world > 2 && !(count & 1) && !(reinterpret_cast<uintptr_t>(d_y) & 15) && !getenv("SIMU_B200_PEER_ONESHOT");
-    if (two_shot) {
-        p->barrier_target += 2u * (uint32_t)blocks;
-        double *slices = p->sym + (int64_t)(2 + parity) * count;
-        void *args[] = {(void *)&p->pp, (void *)&p->rank, (void *)&p->world, (void *)&parity, (void *)&epoch, (void *)&count,
-                        (void *)&d_y, (void *)&mine, (void *)&slices, (void *)&p->barrier, (void *)&p->barrier_target};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)peer_allreduce2_kernel, dim3((unsigned)blocks), dim3(kPeerThreads), args, 0, ctx->stream));
-    } else {
-        p->barrier_target += (uint32_t)blocks;
-        void *args[] = {(void *)&p->pp, (void *)&p->rank, (void *)&p->world, (void *)&parity, (void *)&epoch, (void *)&count,
-                        (void *)&d_y, (void *)&mine, (void *)&p->barrier, (void *)&p->barrier_target};
-        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)peer_allreduce_kernel, dim3((unsigned)blocks), dim3(kPeerThreads), args, 0, ctx->stream));
-    }
+    if (p->form >= 0 && p->form != (int)two_shot)
+        return ctx_fail(ctx, SIMU_B200_EINVAL, "peer_allreduce: buffer alignment changed between calls");
+    p->form = (int)two_shot;
+    void *args[] = {(void *)&p->pp, (void *)&p->rank, (void *)&p->world, (void *)&count, (void *)&d_y, (void *)&p->barrier};
+    CUDA_TRY(ctx, cudaLaunchCooperativeKernel(two_shot ? (void *)peer_allreduce2_kernel : (void *)peer_allreduce_kernel,
+                                              dim3((unsigned)blocks), dim3(kPeerThreads), args, 0, ctx->stream));
     ctx->launches += 1;
     return ctx_cuda(ctx, cudaGetLastError(), "peer_allreduce launch");
 }
