@@ -148,7 +148,8 @@ int miss_index_ensure(simu_b200_ctx *ctx)
     const int64_t wpg = ctx->s16_stride >> 2, ngroups = (ctx->panel_rows + 15) >> 4;       // words (samples, padded) per group
     unsigned long long *d_cnt = (unsigned long long *)ctx_scratch(ctx, SCR_MISS_CNT, (size_t)wpg * 8);
     unsigned long long *d_off = (unsigned long long *)ctx_scratch(ctx, SCR_MISS_OFF, (size_t)(wpg + 1) * 8);
-    if (!d_cnt || !d_off) return -SIMU_B200_ENOMEM;
+    // no HBM left for the index (a panel that fills the GPU): the dense plane needs none
+    if (!d_cnt || !d_off) { cudaGetLastError(); ctx->err.clear(); ctx->miss_state = 2; return 0; }
     auto fail = [&](cudaError_t e, const char *what) { return -ctx_cuda(ctx, e, what); };
     cudaError_t e;
     if ((e = cudaMemsetAsync(d_cnt, 0, (size_t)wpg * 8, ctx->stream)) != cudaSuccess) return fail(e, "miss index memset");
@@ -165,7 +166,7 @@ int miss_index_ensure(simu_b200_ctx *ctx)
     const unsigned long long total = off[wpg];
     if ((double)total > kMaxRate * (double)ctx->panel_rows * (double)ctx->n_samples + 1024.0) { ctx->miss_state = 2; return 0; }
     uint32_t *d_ent = (uint32_t *)ctx_scratch(ctx, SCR_MISS_ENT, (size_t)std::max<unsigned long long>(total, 1) * 4);
-    if (!d_ent) return -SIMU_B200_ENOMEM;
+    if (!d_ent) { cudaGetLastError(); ctx->err.clear(); ctx->miss_state = 2; return 0; }
     // offsets, and the fill cursors (= the segment starts) in the count array
     if ((e = cudaMemcpyAsync(d_off, off.data(), (size_t)(wpg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_cnt, d_off, (size_t)wpg * 8, cudaMemcpyDeviceToDevice, ctx->stream)) != cudaSuccess)

@@ -53,6 +53,22 @@ for n, k in ((100_000, 2), (100_000, 1), (500_000, 2), (1, 1), (12_345, 2), (33_
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    # the exchange replayed from a CUDA graph (its epoch lives in device memory, so the launch parameters never change):
+    # fresh data before every replay, compared with NCCL as above
+    yg = torch.zeros(count, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=stream):
+        ctx.peer_allreduce_dev(yg.data_ptr(), count)
+    for it in range(30):
+        fresh = torch.randn(count, dtype=torch.float64, device=dev, generator=g)
+        ref = fresh.clone()
+        dist.all_reduce(ref)
+        yg.copy_(fresh)
+        graph.replay()
+        worst = max(worst, float((yg - ref).abs().max() / ref.abs().max().clamp_min(1e-300)))
+    torch.cuda.synchronize()
+    del graph
     t_peer = timed(lambda: ctx.peer_allreduce_dev(y.data_ptr(), count))
     t_nccl = timed(lambda: dist.all_reduce(y))
     if worst > 1e-12:
