@@ -295,7 +295,6 @@ __device__ __forceinline__ void weight_item(const double *__restrict__ freq, con
     }
 }
 
-constexpr int kWeightItems = 16;        // per 64-SNP block: 4 groups x 2 planes x 2 traits (K = 1: the first 8)
 template <int K>
 __global__ void __launch_bounds__(128)
 tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
@@ -392,11 +391,6 @@ struct Walk32 {
         tile = tile_b + (blk_b + rot) / nb;
         blk = (blk_b + rot) - (tile - tile_b) * nb;
         left = len - rot;
-    }
-    __device__ __forceinline__ void advance()
-    {
-        if (++blk == nb) { blk = 0; tile++; }
-        if (--left == 0) { tile = tile_b; blk = blk_b; }
     }
 };
 
