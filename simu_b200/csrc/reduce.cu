@@ -264,6 +264,7 @@ liability_split_kernel(const double *__restrict__ y, int64_t n, int64_t k, uint3
     __shared__ uint32_t warp_sums[kSelThreads / 32];
     __shared__ uint64_t s_prefix;
     __shared__ int64_t s_rank;
+    __shared__ uint32_t s_count;
     const int lane = threadIdx.x & 31;
     const int64_t gthreads = (int64_t)gridDim.x * blockDim.x;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,7 +309,7 @@ liability_split_kernel(const double *__restrict__ y, int64_t n, int64_t k, uint3
         grid_barrier(barrier, ++phase * gridDim.x);
         if (threadIdx.x < 32) {                       // every block picks the digit for itself
             int64_t carry = 0, found_rank = -1;
-            uint32_t found_d = 0;
+            uint32_t found_d = 0, found_count = 0;
             uint32_t bins[8];
 #pragma unroll
             for (int q = 0; q < 8; q++) bins[q] = __ldcg(&ghist[pass * 256 + 32 * q + lane]);   // one L2 round trip
@@ -329,15 +330,22 @@ liability_split_kernel(const double *__restrict__ y, int64_t n, int64_t k, uint3
                     const uint32_t excl = __shfl_sync(0xFFFFFFFFu, incl - v, src);
                     found_d = (uint32_t)(d0 + src);
                     found_rank = rank - (carry + excl);
+                    found_count = __shfl_sync(0xFFFFFFFFu, v, src);
                 }
                 carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
-            if (lane == 0) { s_prefix = prefix | ((uint64_t)found_d << shift); s_rank = found_rank; }
+            if (lane == 0) { s_prefix = prefix | ((uint64_t)found_d << shift); s_rank = found_rank; s_count = found_count; }
         }
         __syncthreads();
         prefix = s_prefix;
         rank = s_rank;                                // = number of keys equal so far that sort before rank k
+        const uint32_t candidates = s_count;
         __syncthreads();
+        // ONE key is left under this prefix: it is T, and its lower digits are not needed -- every other key differs
+        // from it in the digits found so far, so comparing with the prefix (lower digits zero) classifies them, and T
+        // itself (>= prefix, rank 0 among its equals) falls on the case side as it must.  Continuous liabilities get
+        // here after 3 passes instead of 8; ties run all passes.  (Every block sees the same histogram: uniform exit.)
+        if (candidates == 1) break;
     }
     // prefix = T; rank = how many of the keys equal to T belong to the controls (lowest sample indices first).
     // Each block owns a contiguous range of samples, each thread a contiguous sub-range.
