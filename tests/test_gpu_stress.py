@@ -87,3 +87,54 @@ def test_many_contexts_and_reuse():
                 assert np.max(np.abs(e - f)) <= 1e-5 * max(np.max(np.abs(e)), 1e-300)
     finally:
         a.close(); b.close()
+
+
+@pytest.mark.parametrize("seed", range(14))
+def test_sample16_random_shapes_all_paths_against_oracle(seed, monkeypatch):
+    """Random SAMPLE16 shapes, missing rates and missingness patterns (none at all, a bad sample, a bad SNP): both counts
+    kernels, EXACT (parameter-bank kernel) and FAST with the dense plane and with the sparse missing-genotype index,
+    each against the oracle; prefix calls (mc smaller than the panel) included."""
+    from oracle import oracle
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.choice([1, 2, 31, 33, 127, 129, 767, 769, 1000, 2049, 4097, 6001]))
+    mc = int(rng.choice([1, 15, 16, 17, 63, 65, 127, 129, 200, 513, 1537, 3001]))
+    rate = float(rng.choice([0.0, 0.001, 0.003]))
+    codes = rng.choice(3, size=(mc, n), p=[0.5, 0.3, 0.2]).astype(np.uint8)       # snp_t codes 0 / 1 / 2 (bed.c:75-85), 3 = missing
+    codes[rng.random((mc, n)) < rate] = 3
+    if seed % 3 == 1 and n > 8:
+        codes[:, n // 2] = 3                                                       # a sample with every genotype missing
+    if seed % 3 == 2 and mc > 4:
+        codes[mc // 3, :] = 3                                                      # a SNP with every genotype missing
+    rows = np.stack([oracle.pack(codes[j]) for j in range(mc)])
+    x1 = rng.standard_normal(mc)
+    x2 = rng.standard_normal(mc) if seed % 2 else None
+    oc, of = oracle.find_freq(rows, n)
+    o1, o2 = oracle.find_pheno(rows, n, of, x1, x2)
+    scale1 = max(np.max(np.abs(o1)), 1e-300)
+    pre = max(1, mc // 2)
+    p1, _ = oracle.find_pheno(rows[:pre], n, of[:pre], x1[:pre], None)
+    for counts_kernel in ("tma", "reg"):
+        monkeypatch.setenv("SIMU_B200_COUNTS", counts_kernel)
+        with capi.Context(n) as ctx:
+            ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+            ctx.panel_put_rows(0, rows)
+            counts, freq = ctx.find_freq()
+            assert np.array_equal(counts, oc) and np.array_equal(freq, of)
+    monkeypatch.delenv("SIMU_B200_COUNTS")
+    for form in ("SIMU_B200_TC_DENSE", "SIMU_B200_TC_SPARSE"):
+        monkeypatch.setenv(form, "1")
+        with capi.Context(n) as ctx:
+            ctx.panel_alloc(mc, capi.LAYOUT_SAMPLE16)
+            ctx.panel_put_rows(0, rows)
+            e1, e2 = ctx.find_pheno(of, x1, x2, mode=capi.MODE_EXACT)
+            assert np.array_equal(e1, o1) and (x2 is None or np.array_equal(e2, o2))
+            for _ in range(2):                                                     # the index (if any) is built at the second call
+                f1, f2 = ctx.find_pheno(of, x1, x2, mode=capi.MODE_FAST)
+                assert np.max(np.abs(f1 - o1)) <= 1e-9 * scale1 + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x1))
+                if x2 is not None:
+                    assert np.max(np.abs(f2 - o2)) <= 1e-9 * max(np.max(np.abs(o2)), 1e-300) + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x2))
+            state = ctx.missing_index()[0]
+            assert state == 2 if form.endswith("DENSE") else state in (1, 2)       # 2: above the 0.4 % limit (bad sample / SNP on a small panel)
+            q1, _ = ctx.find_pheno(of[:pre], x1[:pre], None, mode=capi.MODE_FAST)  # a prefix of the panel
+            assert np.max(np.abs(q1 - p1)) <= 1e-9 * max(np.max(np.abs(p1)), 1e-300) + 9.0 * mc * 2.0 ** -41 * np.max(np.abs(x1))
+        monkeypatch.delenv(form)
