@@ -636,6 +636,9 @@ def run_ours(args, w):
                        "step": "find_freq -> effect scaling on the device -> find_pheno -> apply_heritability per trait" if wl.one_call
                                else "find_freq -> find_pheno -> apply_heritability per trait" + (" -> liability split" if w["cc"] else ""),
                        "cuda_graph": res["cuda_graph"], "missing_genotypes": res["missing_genotypes"],
+                       "resident_panel": "everything that depends on the panel alone is staging, not step: the SAMPLE16 transposition and, from "
+                                         "the panel's second use, the index of its missing genotypes; allele counts are recomputed every step; "
+                                         "the e2e leg re-stages the panel every step and therefore runs find_pheno with the dense missing-genotype plane",
                        "l2": f"inputs larger than L2 ({mc * B / 1e6:.0f} MB of causal rows per pass, 126 MB L2)",
                        "parallelism": f"snp-shard x{world}, 1 all-reduce ({wl.allreduce})" if world > 1 else "single GPU"},
             "bed_gbs": res["bed_gbs"],
