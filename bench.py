@@ -429,7 +429,9 @@ class Workload:
         _, bytes_counts, bytes_pheno = alg_bytes(w)
         peaks, peak_src = _peaks()
         names = KERNEL_NAMES[self.args.layout]
-        if self.args.layout == "s16" and (mc + 15) // 16 < 8 * 2 * torch.cuda.get_device_properties(self.dev).multi_processor_count * 8:
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        groups = (mc + 15) // 16
+        if self.args.layout == "s16" and groups < 8 * 2 * sms * 8 and groups * ((ctx.group_stride + 8191) // 8192) >= 2 * sms * 8:
             names = ("counts_s16_tma_kernel",) + names[1:]      # the library's own choice by shape (counts_s16.cu)
         fast = self.mode == self.capi.MODE_FAST
         miss_state, miss_entries = ctx.missing_index() if self.args.layout == "s16" else (0, 0)

@@ -431,7 +431,10 @@ int launch_counts_s16(simu_b200_ctx *ctx, cudaStream_t stream, int64_t mc, int32
     // its balanced contiguous ranges wins (config 2: 0.375 against 0.428 ms, config 3: 0.055 against 0.067 ms).
     // SIMU_B200_COUNTS=reg|tma forces one of them (A/B runs).
     const char *force = getenv("SIMU_B200_COUNTS");
-    const bool tma = force ? force[0] == 't' : groups < 8 * max_blocks * kWarps;
+    // ... and a panel of fewer chunks than two per warp of the ring kernel is launch-bound either way; the register-fed kernel
+    // has the shorter prologue there (config 1: 13.5 against 16 us)
+    const int64_t chunks = groups * ((ctx->s16_stride + kSlotBytes - 1) / kSlotBytes);
+    const bool tma = force ? force[0] == 't' : (groups < 8 * max_blocks * kWarps && chunks >= 2 * (int64_t)ctx->num_sms * kWarpsT);
     if (tma) return launch_counts_s16_tma(ctx, stream, mc, d_counts, d_freq);
     const int64_t resident = max_blocks * kWarps;
     // static grid-stride assignment: aim at >= 8 (group, sample range) tasks per resident warp so that the last,
