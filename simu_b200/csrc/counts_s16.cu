@@ -226,8 +226,9 @@ constexpr int kSmemT = kWarpsT * kRing * kSlotBytes + kWarpsT * kRing * 8;
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// two rounds (16 vectors per lane) of one slot -> two weight-32 words per tree; vectors >= nv read as zero
-template <int NLEV>
+// two rounds (16 vectors per lane) of one slot -> two weight-32 words per tree; vectors >= nv read as zero (FULL: the
+// slot holds all 512 vectors and the loads carry no predicate -- 16 compares and 32 register clears less per slot)
+template <int NLEV, bool FULL>
 __device__ __forceinline__ void slot_rounds(uint32_t slot, int lane, int nv, Sliced<NLEV> &R, Sliced<NLEV> &A, uint32_t (&r32)[2], uint32_t (&a32)[2])
 {
 #pragma unroll
@@ -237,7 +238,7 @@ __device__ __forceinline__ void slot_rounds(uint32_t slot, int lane, int nv, Sli
         for (int q = 0; q < 8; q++) {
             const int v = (8 * h + q) * 32 + lane;
             uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0;
-            if (v < nv) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(slot + 16u * (uint32_t)v));
+            if (FULL || v < nv) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(slot + 16u * (uint32_t)v));
             w[4 * q] = x0; w[4 * q + 1] = x1; w[4 * q + 2] = x2; w[4 * q + 3] = x3;
         }
 #pragma unroll
@@ -336,12 +337,15 @@ counts_s16_tma_kernel(const S16Tma p)
             uint32_t r2[2], a2[2], cr, ca;
             const int nv = (int)(chunk_bytes(c) >> 4);
             wait_slot();
-            slot_rounds<NLEV>(ring + (uint32_t)(slot * kSlotBytes), lane, nv, R, A, r2, a2);
+            if (nv == kSlotVecs) slot_rounds<NLEV, true>(ring + (uint32_t)(slot * kSlotBytes), lane, nv, R, A, r2, a2);
+            else slot_rounds<NLEV, false>(ring + (uint32_t)(slot * kSlotBytes), lane, nv, R, A, r2, a2);
             next_slot();
             csa(R.lvl[5], cr, R.lvl[5], r2[0], r2[1]);
             csa(A.lvl[5], ca, A.lvl[5], a2[0], a2[1]);
-            R.template ripple<6>(cr, nlev);
-            A.template ripple<6>(ca, nlev);
+            // all NLEV levels, unconditionally: skipping the levels N cannot reach costs a select per level and tree
+            // (61 SEL + 25 ISETP per slot against the 12 LOP3 it saved for N = 100K)
+            R.template ripple<6>(cr, NLEV);
+            A.template ripple<6>(ca, NLEV);
         }
         // the piece's counts: lanes' counters added, lane p extracts bit position p
 #pragma unroll
