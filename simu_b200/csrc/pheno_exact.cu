@@ -328,6 +328,121 @@ pheno_exact_s16p_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, i
     }
 }
 
+// SAMPLE16, third form (the default): TWO samples per thread, one warp per block, effects interleaved by trait.
+//
+// ncu on the kernel above (profiles/r02f_exact_s16p_ncu.txt): 10.8 issued instructions per 32 samples and SNP at
+// 71 % of the issue slots, FP64 pipe 51 %, shared-memory pipe 52 % -- issue-bound before either data pipe.  Per 64
+// samples and SNP this form issues 2 LDS.64 + 2 (SHF + LOP3) + ONE LDCU.128 (both traits' effects) + 4 DMUL + 4 DADD:
+// the uniform loads, the loop bookkeeping and the table build are shared by twice the samples, and a warp carries
+// four independent addition chains instead of two.  Same operations in the same order per sample -> same bits.
+// One warp per block keeps the block count at N/64 (1563 for 100K samples = 10.6 per SM; 64-thread blocks of two
+// samples per thread would be 5.3 per SM, a 14 % tail) (the kernel is compiled for up to 64 threads).
+template <int K> struct alignas(16) ExactEffectsI { static constexpr int kSnps = (K == 2) ? 1536 : 3072; double x[kSnps][K]; };
+
+template <int K>
+__global__ void __launch_bounds__(64)   // launched with 32: ptxas gives up the uniform datapath (LDCU, DMUL R, R, UR) for kernels bounded to one warp
+pheno_exact_s16d_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int mc, int64_t n_samples,
+                        const double *__restrict__ freq, double *__restrict__ y1, double *__restrict__ y2, int accumulate, int pdl,
+                        const __grid_constant__ ExactEffectsI<K> eff)
+{
+    __shared__ __align__(16) double tbl[2][kChunk][4];        // [buffer][snp][dosage code] -> a - 2f, missing -> +0.0
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;        // samples i0, i0 + 1 (the pitch covers round_up(N, 128))
+    const bool act0 = i0 < n_samples, act1 = i0 + 1 < n_samples;
+    const uint2 *base = reinterpret_cast<const uint2 *>(panel) + (act0 ? (i0 >> 1) : 0);
+    const int64_t gw = s16_stride >> 3;                       // 8-byte words per group
+    // the frequencies of a chunk are loaded one chunk ahead (two per thread of a 32-thread block) and turned into the
+    // table at the END of the chunk before: ncu showed the load -> first use latency of a build at the top of a chunk
+    // as the kernel's top stall (14 % of the samples) with 2.6 warps per scheduler
+    double fr[2];
+    auto load_freq = [&](int j0) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int t = threadIdx.x + u * blockDim.x;
+            fr[u] = (t < kChunk && j0 + t < mc) ? __ldg(freq + j0 + t) : 0.0;
+        }
+    };
+    auto build = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int t = threadIdx.x + u * blockDim.x;
+            if (t < kChunk) {
+                const double avg = __dmul_rn(2.0, fr[u]);     // source.cc:986
+                *reinterpret_cast<double2 *>(&tbl[buf][t][0]) = make_double2(__dsub_rn(2.0, avg), __dsub_rn(1.0, avg));
+                *reinterpret_cast<double2 *>(&tbl[buf][t][2]) = make_double2(__dsub_rn(0.0, avg), 0.0);
+            }
+        }
+    };
+    uint2 w[4], wn[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) w[q] = (16 * q < mc) ? __ldg(base + q * gw) : make_uint2(0u, 0u);
+    load_freq(0);
+    build(0);
+    // launched with programmatic stream serialisation behind the previous slice of the same call (pdl != 0): the launch
+    // itself, the frequency loads and the first table overlap that slice's tail (ptxas sinks the word loads below the
+    // wait); the previous slice's sums are visible after the wait
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    double acc[2][K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        acc[0][k] = (accumulate && act0) ? (k == 0 ? y1[i0] : y2[i0]) : 0.0;
+        acc[1][k] = (accumulate && act1) ? (k == 0 ? y1[i0 + 1] : y2[i0 + 1]) : 0.0;
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    int buf = 0;
+    for (int j0 = 0; j0 < mc; j0 += kChunk, buf ^= 1) {
+        const int nj = min(kChunk, mc - j0);
+        __syncthreads();                                        // table `buf` is complete, table `buf ^ 1` is no longer read
+        load_freq(j0 + kChunk);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            wn[q] = (j0 + kChunk + 16 * q < mc) ? __ldg(base + ((j0 + kChunk) / 16 + q) * gw) : make_uint2(0u, 0u);
+        const char *tb = reinterpret_cast<const char *>(&tbl[buf][0][0]);
+        if (nj == kChunk) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+#pragma unroll
+                for (int f = 0; f < 16; f++) {
+                    const int jj = 16 * q + f;
+                    // byte offset of the table entry: the 2-bit code times 8
+                    const uint32_t o0 = (f == 0) ? (w[q].x << 3) & 24u : (f == 1) ? (w[q].x << 1) & 24u : (w[q].x >> (2 * f - 3)) & 24u;
+                    const uint32_t o1 = (f == 0) ? (w[q].y << 3) & 24u : (f == 1) ? (w[q].y << 1) & 24u : (w[q].y >> (2 * f - 3)) & 24u;
+                    const double t0 = *reinterpret_cast<const double *>(tb + jj * 32 + o0);
+                    const double t1 = *reinterpret_cast<const double *>(tb + jj * 32 + o1);
+                    double x[2];
+                    if (K == 2) *reinterpret_cast<double2 *>(x) = *reinterpret_cast<const double2 *>(&eff.x[j0 + jj][0]);   // one LDCU.128
+                    else x[0] = eff.x[j0 + jj][0];
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        acc[0][k] = __dadd_rn(acc[0][k], __dmul_rn(t0, x[k]));   // source.cc:994-995
+                        acc[1][k] = __dadd_rn(acc[1][k], __dmul_rn(t1, x[k]));
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                for (int f = 0; f < 16 && 16 * q + f < nj; f++) {       // w[q] with a static index: the words stay in registers
+                    const int jj = 16 * q + f;
+                    const uint32_t o0 = ((w[q].x >> (2 * f)) & 3u) * 8u, o1 = ((w[q].y >> (2 * f)) & 3u) * 8u;
+                    const double t0 = *reinterpret_cast<const double *>(tb + jj * 32 + o0);
+                    const double t1 = *reinterpret_cast<const double *>(tb + jj * 32 + o1);
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const double x = eff.x[j0 + jj][k];
+                        acc[0][k] = __dadd_rn(acc[0][k], __dmul_rn(t0, x));
+                        acc[1][k] = __dadd_rn(acc[1][k], __dmul_rn(t1, x));
+                    }
+                }
+            }
+        }
+        build(buf ^ 1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) w[q] = wn[q];
+    }
+    if (act0) { y1[i0] = acc[0][0]; if (K == 2) y2[i0] = acc[0][K - 1]; }
+    if (act1) { y1[i0 + 1] = acc[1][0]; if (K == 2) y2[i0 + 1] = acc[1][K - 1]; }
+}
+
 template <int K, int SPT>
 void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const double *d_freq, const double *d_x1,
                     const double *d_x2, double *d_y1, double *d_y2)
@@ -344,6 +459,40 @@ void launch_exact_t(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, const
     else
         pheno_exact_kernel<K, SPT><<<(unsigned)blocks, threads, 0, ctx->stream>>>(
             ctx->panel, ctx->row_stride, d_rows, mc, ctx->n_samples, d_freq, d_x1, d_x2, d_y1, d_y2);
+}
+
+template <int K>
+int launch_exact_s16d(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *hx1, const double *hx2, double *d_y1,
+                      double *d_y2, int accumulate)
+{
+    using Eff = ExactEffectsI<K>;
+    const int64_t blocks = (ctx->n_samples + 63) / 64;
+    std::unique_ptr<Eff> effp(new (std::nothrow) Eff);        // host staging of one launch's parameters
+    if (!effp) return ctx_fail(ctx, SIMU_B200_ENOMEM, "find_pheno: out of host memory");
+    Eff &eff = *effp;
+    memset(&eff, 0, sizeof(eff));
+    static const bool use_pdl = getenv("SIMU_B200_EXACT_NOPDL") == nullptr;     // A/B runs
+    for (int64_t j0 = 0; j0 < mc; j0 += Eff::kSnps) {
+        const int n = (int)std::min<int64_t>(Eff::kSnps, mc - j0);
+        for (int j = 0; j < n; j++) {
+            eff.x[j][0] = hx1[j0 + j];
+            if (K == 2) eff.x[j][K - 1] = hx2[j0 + j];
+        }
+        // every slice after the first overlaps its prologue (genotype words, frequencies, first table) with the tail of
+        // the slice before it; the first one follows kernels whose output it reads in that prologue and is launched plainly
+        const int pdl = (j0 > 0 && use_pdl) ? 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(32); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+        CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, pheno_exact_s16d_kernel<K>, (const uint8_t *)(ctx->panel + (j0 / 16) * ctx->s16_stride),
+                                         (int64_t)ctx->s16_stride, n, (int64_t)ctx->n_samples, (const double *)(d_freq + j0), d_y1, d_y2,
+                                         (accumulate || j0 > 0) ? 1 : 0, pdl, eff));
+        ctx->launches++;
+    }
+    return SIMU_B200_OK;
 }
 
 }  // namespace
@@ -399,7 +548,12 @@ int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq,
         hx1 = ctx->h_eff; hx2 = k2 ? ctx->h_eff + mc : nullptr;
     }
     const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
-    if (param_kernel) {
+    static const bool one_sample = getenv("SIMU_B200_EXACT_V") && atoi(getenv("SIMU_B200_EXACT_V")) == 0;   // A/B runs: one sample per thread
+    if (param_kernel && !one_sample) {
+        const int rc = k2 ? launch_exact_s16d<2>(ctx, mc, d_freq, hx1, hx2, d_y1, d_y2, accumulate)
+                          : launch_exact_s16d<1>(ctx, mc, d_freq, hx1, nullptr, d_y1, nullptr, accumulate);
+        if (rc) return rc;
+    } else if (param_kernel) {
         const int64_t blocks = (ctx->n_samples + kThreadsP - 1) / kThreadsP;
         std::unique_ptr<ExactEffects> effp(new (std::nothrow) ExactEffects);      // host staging of one launch's parameters
         if (!effp) return ctx_fail(ctx, SIMU_B200_ENOMEM, "find_pheno: out of host memory");
