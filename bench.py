@@ -344,9 +344,7 @@ class Workload:
             else:
                 self.dist.all_reduce(d_y)
         for t in range(k):
-            ctx.sumsq_dev(d_y[t].data_ptr(), n, self.d_misc[t].data_ptr())
-            ctx.heritability_dev(HSQ[t], d_y[t].data_ptr(), n, self.d_noise[t].data_ptr(), self.d_misc[t].data_ptr(),
-                                 self.d_misc[4 + 2 * t].data_ptr())
+            ctx.apply_heritability_dev(HSQ[t], d_y[t].data_ptr(), n, self.d_noise[t].data_ptr(), self.d_misc[4 + 2 * t].data_ptr())
         if w["cc"]:      # default --ncas/--ncon: both pools fully labelled -> the order statistic decides
             if self.args.cc_sort:
                 ctx.liability_order_dev(d_y[0].data_ptr(), n, self.d_index.data_ptr())

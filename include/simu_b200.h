@@ -286,6 +286,11 @@ SIMU_B200_API int simu_b200_sumsq_dev(simu_b200_ctx *ctx, const double *d_y, int
  * d_coef[0..1]; then y = y*gen + noise*env (source.cc:1027). */
 SIMU_B200_API int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n,
                                              const double *d_noise, const double *d_sumsq, double *d_coef);
+/* apply_heritability (source.cc:1008-1029) on device-resident data in ONE launch: sum of squares,
+ * coefficients (written to d_coef[0..1] when not NULL) and y = y*gen + noise*env.  Same result as
+ * simu_b200_sumsq_dev followed by simu_b200_heritability_dev up to the order of the sum of squares. */
+SIMU_B200_API int simu_b200_apply_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n,
+                                                   const double *d_noise, double *d_coef);
 SIMU_B200_API int simu_b200_liability_order_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,
                                                 int32_t *d_index);
 SIMU_B200_API int simu_b200_liability_split_dev(simu_b200_ctx *ctx, const double *d_pheno, int64_t n,

@@ -64,6 +64,7 @@ SIGNATURES = {
     "simu_b200_find_pheno_dev": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i32]),
     "simu_b200_sumsq_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "simu_b200_heritability_dev": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp, _vp]),
+    "simu_b200_apply_heritability_dev": (_i32, [_vp, _f32, _vp, _i64, _vp, _vp]),
     "simu_b200_liability_order_dev": (_i32, [_vp, _vp, _i64, _vp]),
     "simu_b200_peer_init": (_i32, [_vp, _i32, _i32, _i64, _vp]),
     "simu_b200_peer_connect": (_i32, [_vp, _vp]),
@@ -370,6 +371,10 @@ class Context:
 
     def sumsq_dev(self, d_y, n, d_out):
         self._check(self.lib.simu_b200_sumsq_dev(self.h, C.c_void_p(d_y), n, C.c_void_p(d_out)))
+
+    def apply_heritability_dev(self, hsq, d_y, n, d_noise, d_coef=None):
+        self._check(self.lib.simu_b200_apply_heritability_dev(self.h, hsq, C.c_void_p(d_y), n, C.c_void_p(d_noise),
+                                                              C.c_void_p(d_coef or 0)))
 
     def heritability_dev(self, hsq, d_y, n, d_noise, d_sumsq, d_coef):
         self._check(self.lib.simu_b200_heritability_dev(self.h, hsq, C.c_void_p(d_y), n, C.c_void_p(d_noise),

@@ -658,6 +658,14 @@ int simu_b200_sumsq_dev(simu_b200_ctx *ctx, const double *d_y, int64_t n, double
     return launch_sumsq(ctx, d_y, n, d_out);
 }
 
+int simu_b200_apply_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise, double *d_coef)
+{
+    if (!ctx) return SIMU_B200_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (!d_y || !d_noise || n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "apply_heritability_dev: bad arguments");
+    return launch_apply_heritability(ctx, hsq, d_y, n, d_noise, d_coef);
+}
+
 int simu_b200_heritability_dev(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
                                const double *d_sumsq, double *d_coef)
 {
@@ -896,8 +904,7 @@ int simu_b200_apply_heritability(simu_b200_ctx *ctx, float hsq, double *pheno, i
     if ((rc = h2d(ctx, SCR_NOISE, noise, (size_t)n * 8, &d_noise))) return rc;
     double *d_misc = (double *)ctx_scratch(ctx, SCR_COUNTS, 64);
     if (!d_misc) return SIMU_B200_ENOMEM;
-    if ((rc = launch_sumsq(ctx, (const double *)d_y, n, d_misc))) return rc;
-    if ((rc = launch_heritability(ctx, hsq, (double *)d_y, n, (const double *)d_noise, d_misc, d_misc + 1))) return rc;
+    if ((rc = launch_apply_heritability(ctx, hsq, (double *)d_y, n, (const double *)d_noise, d_misc + 1))) return rc;
     double coef[2] = {0, 0};
     CUDA_TRY(ctx, cudaMemcpyAsync(pheno, d_y, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(coef, d_misc + 1, 16, cudaMemcpyDeviceToHost, ctx->stream));

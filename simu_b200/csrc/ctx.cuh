@@ -72,7 +72,7 @@ struct simu_b200_ctx {
 enum ScratchSlot {
     SCR_ROWS = 0, SCR_COUNTS, SCR_FREQ, SCR_X1, SCR_X2, SCR_Y1, SCR_Y2, SCR_NOISE,
     SCR_LUT, SCR_YPART, SCR_SORT, SCR_MISC, SCR_FUSED, SCR_RAW1, SCR_RAW2, SCR_SPOW, SCR_SYNC, SCR_DEBUG, SCR_TCW,
-    SCR_MISS_CNT, SCR_MISS_ENT, SCR_MISS_OFF, SCR_WMFIX, SCR_CORR, SCR_CNTACC
+    SCR_MISS_CNT, SCR_MISS_ENT, SCR_MISS_OFF, SCR_WMFIX, SCR_CORR, SCR_CNTACC, SCR_HERIT
 };
 
 int ctx_fail(simu_b200_ctx *ctx, int code, const char *fmt, ...);
@@ -126,6 +126,8 @@ int launch_pheno_lut(simu_b200_ctx *ctx, const int32_t *d_rows, int64_t mc, cons
 
 // kernel (c): reductions.  reduce.cu
 int launch_sumsq(simu_b200_ctx *ctx, const double *d_y, int64_t n, double *d_out);
+// sum of squares + coefficients + scaling in one cooperative launch (coefficients to d_coef[0..1] when not NULL)
+int launch_apply_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise, double *d_coef);
 int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise,
                         const double *d_sumsq, double *d_coef);
 int launch_argsort_f64(simu_b200_ctx *ctx, const double *d_key, int64_t n, int32_t *d_index);
@@ -150,3 +152,25 @@ int launch_unpanel(simu_b200_ctx *ctx, int64_t src_row, int64_t n_rows, uint8_t 
 // as packed rows at dst + r * dst_pitch (dst_pitch a multiple of 4).  synth.cu
 int launch_synth(simu_b200_ctx *ctx, uint64_t seed, int64_t first_row, const int64_t *d_row_ids, int64_t n_rows,
                  uint8_t *dst, int64_t dst_pitch);
+
+// One grid-wide barrier inside a cooperative launch (all blocks co-resident) that cleans up after itself: the last block to
+// leave zeroes both counters, so a kernel's launch parameters never change and it replays inside a CUDA graph.
+__device__ __forceinline__ void grid_barrier_once(unsigned int *bar /* [2], zero between launches */)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&bar[0], 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while (v < gridDim.x);
+        if (atomicAdd(&bar[1], 1u) == gridDim.x - 1u) {      // everyone has seen the full count: reset for the next launch
+            bar[0] = 0u;
+            bar[1] = 0u;
+            __threadfence();
+        }
+    }
+    __syncthreads();
+}
+

@@ -305,6 +305,84 @@ tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1
     if (item < ntiles * (8 * K)) weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)), wm_fix);
 }
 
+// both passes in ONE cooperative launch (default above kSmallMc): every block sums / maximises its strided share, the blocks
+// meet at a grid barrier, EVERY block reduces the per-block partials in the same fixed order (so all of them hold the same
+// exponents without another round trip) and goes on to its share of the weight tiles.  Replaces memset + tc_prepare_kernel
+// + tc_weights_kernel (29 us of a 0.81 ms step on config 2, 28 us of 0.17 ms on config 3: two launches, a serial
+// last-block loop over 128 partials and a ticket).  The barrier cleans up after itself: the last block to leave zeroes both
+// counters, so the launch parameters never change and the step still replays as one CUDA graph.
+constexpr int kFusedThreads = 256;
+template <int K>
+__global__ void __launch_bounds__(kFusedThreads)
+tc_weights_fused_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
+                        int64_t ntiles, double *__restrict__ partial /* [K][grid] sums, then [K][grid] maxima */,
+                        unsigned int *__restrict__ bar, TcScale *__restrict__ scale, uint8_t *__restrict__ wt,
+                        long long *__restrict__ wm_fix)
+{
+    __shared__ double ssum[K][kFusedThreads], smax[K][kFusedThreads];
+    const int G = (int)gridDim.x;                                  // <= kFusedThreads (host)
+    double sum[K], mx[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { sum[k] = 0.0; mx[k] = 0.0; }
+    for (int64_t j = (int64_t)blockIdx.x * kFusedThreads + threadIdx.x; j < mc; j += (int64_t)G * kFusedThreads) {
+        const double f = freq[j];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            double wp, wm, c;
+            weights_of(f, k == 0 ? x1[j] : x2[j], wp, wm, c);
+            sum[k] += c;
+            mx[k] = fmax(mx[k], fmax(fabs(wp), fabs(wm)));
+        }
+    }
+    auto tree = [&]() {                                            // fixed shape: deterministic for a given grid
+        __syncthreads();
+        for (int s = kFusedThreads / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) {
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    ssum[k][threadIdx.x] += ssum[k][threadIdx.x + s];
+                    smax[k][threadIdx.x] = fmax(smax[k][threadIdx.x], smax[k][threadIdx.x + s]);
+                }
+            }
+            __syncthreads();
+        }
+    };
+#pragma unroll
+    for (int k = 0; k < K; k++) { ssum[k][threadIdx.x] = sum[k]; smax[k][threadIdx.x] = mx[k]; }
+    tree();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            partial[k * G + blockIdx.x] = ssum[k][0];
+            partial[(K + k) * G + blockIdx.x] = smax[k][0];
+        }
+    }
+    grid_barrier_once(bar);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const bool in = (int)threadIdx.x < G;
+        ssum[k][threadIdx.x] = in ? __ldcg(partial + k * G + threadIdx.x) : 0.0;
+        smax[k][threadIdx.x] = in ? __ldcg(partial + (K + k) * G + threadIdx.x) : 0.0;
+    }
+    tree();
+    int e[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double m = smax[k][0];
+        // |W| < 2^(ilogb(m) + 1)  ->  |W| / 2^e < 2^kFracBits
+        e[k] = (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 - kFracBits : 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < K) {
+        const int k = threadIdx.x;
+        scale[k].constant = ssum[k][0];
+        scale[k].exponent = e[k];
+        scale[k].pad = 0;
+    }
+    const double inv_quantum[2] = {ldexp(1.0, -e[0]), K == 2 ? ldexp(1.0, -e[1]) : 0.0};
+    for (int64_t item = (int64_t)blockIdx.x * kFusedThreads + threadIdx.x; item < ntiles * (8 * K); item += (int64_t)G * kFusedThreads)
+        weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)), wm_fix);
+}
+
 // both passes in ONE CTA for small causal sets (the sparse configs are launch-bound: two dependent launches and a
 // grid-wide ticket cost more than the arithmetic).  Same summation order as nothing else: the constant is a sum
 // over a fixed strided partition followed by a fixed tree, so it is deterministic for a given mc.
@@ -690,13 +768,20 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     // weight tiles, then: [TcScale x 2][ticket + pad][partials 4 x kPrepBlocks doubles]
     const size_t wt_bytes = (size_t)nblocks * kHalves * kWTileBytes;
     const size_t aux_off = (wt_bytes + 255) & ~(size_t)255;
-    uint8_t *wt = (uint8_t *)ctx_scratch(ctx, SCR_TCW, aux_off + 64 + 4 * kPrepBlocks * sizeof(double));
+    static_assert(kFusedThreads >= kPrepBlocks, "partials");
+    uint8_t *wt = (uint8_t *)ctx_scratch(ctx, SCR_TCW, aux_off + 64 + 4 * kFusedThreads * sizeof(double));
     const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
     double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
     if (!wt || !ypart) return SIMU_B200_ENOMEM;
     TcScale *scale = reinterpret_cast<TcScale *>(wt + aux_off);
     unsigned int *ticket = reinterpret_cast<unsigned int *>(wt + aux_off + 32);
     double *partial = reinterpret_cast<double *>(wt + aux_off + 64);
+    // the fused weight kernel's barrier counters: zero between launches (the kernel resets them), cleared when first allocated
+    static const bool use_fused = getenv("SIMU_B200_TC_WEIGHTS_SPLIT") == nullptr;     // A/B runs: the two-kernel form
+    const bool fbar_fresh = ctx->scratch_bytes[SCR_FUSED] < 64;
+    unsigned int *fbar = (unsigned int *)ctx_scratch(ctx, SCR_FUSED, 64);
+    if (!fbar) return SIMU_B200_ENOMEM;
+    if (fbar_fresh) CUDA_TRY(ctx, cudaMemsetAsync(fbar, 0, 64, ctx->stream));
     if (!ctx->tc_attr_set) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(pheno_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -711,6 +796,17 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     int ps = prof_begin(ctx, PROF_LUT_BUILD);
     if (mc <= kSmallMc) {
         tc_small_prepare_kernel<K><<<1, kSmallThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt, wm_fix);
+    } else if (use_fused) {
+        const int64_t items = nblocks * kHalves * 8 * K, most = items > mc ? items : mc;
+        int64_t fgrid = (most + kFusedThreads - 1) / kFusedThreads;
+        const int64_t fmax_grid = ctx->num_sms < kFusedThreads ? ctx->num_sms : kFusedThreads;     // co-resident, and one partial per thread
+        if (fgrid > fmax_grid) fgrid = fmax_grid;
+        const int64_t ntiles = nblocks * kHalves;
+        const double *a_freq = d_freq, *a_x1 = d_x1, *a_x2 = d_x2;
+        int64_t a_mc = mc;
+        void *args[] = {(void *)&a_freq, (void *)&a_x1, (void *)&a_x2, (void *)&a_mc, (void *)&ntiles, (void *)&partial,
+                        (void *)&fbar, (void *)&scale, (void *)&wt, (void *)&wm_fix};
+        CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)tc_weights_fused_kernel<K>, dim3((unsigned)fgrid), dim3(kFusedThreads), args, 0, ctx->stream));
     } else {
         CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
         tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);

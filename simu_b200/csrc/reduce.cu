@@ -85,6 +85,55 @@ heritability_kernel(float hsq, double *__restrict__ y, int64_t n, const double *
         y[i] = __dadd_rn(__dmul_rn(y[i], gen_coef), __dmul_rn(noise[i], env_coef));
 }
 
+// apply_heritability in ONE cooperative launch: per-block sums of squares, a grid barrier, then every block adds the
+// partials in the same fixed order (all blocks hold the same variance without another round trip), forms the coefficients
+// exactly as source.cc:1012-1025 and scales its share.  Replaces sumsq_partial + sum_final + heritability_kernel
+// (11.5 us per trait in the launch list of a 0.81 ms step; the sparse configs are a few launches of microseconds each).
+constexpr int kHerThreads = 256;
+__global__ void __launch_bounds__(kHerThreads)
+heritability_fused_kernel(float hsq, double *__restrict__ y, int64_t n, const double *__restrict__ noise,
+                          double *__restrict__ partial /* [grid] */, unsigned int *__restrict__ bar, double *__restrict__ coef)
+{
+    __shared__ double smem[32];
+    __shared__ double total;
+    const int G = (int)gridDim.x;                                  // <= kHerThreads (host)
+    // a block owns a CONTIGUOUS range, a thread keeps its values in registers across the barrier (up to kHerKeep of them)
+    constexpr int kHerKeep = 4;
+    const int64_t per = (n + G - 1) / G, lo = (int64_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+    double keep[kHerKeep];
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < kHerKeep; u++) {
+        const int64_t i = lo + (int64_t)u * kHerThreads + threadIdx.x;
+        keep[u] = i < hi ? y[i] : 0.0;
+        s += keep[u] * keep[u];
+    }
+    for (int64_t i = lo + (int64_t)kHerKeep * kHerThreads + threadIdx.x; i < hi; i += kHerThreads) { const double v = y[i]; s += v * v; }
+    s = block_sum(s, smem);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    grid_barrier_once(bar);
+    s = (int)threadIdx.x < G ? __ldcg(partial + threadIdx.x) : 0.0;
+    s = block_sum(s, smem);
+    if (threadIdx.x == 0) total = s;
+    __syncthreads();
+    const double pheno_var = total / static_cast<double>(n);                  // source.cc:1012
+    double gen_coef, env_coef;
+    if ((fabs((double)hsq) <= (double)FLT_EPSILON) || (fabs(pheno_var) <= (double)FLT_EPSILON)) {
+        gen_coef = 0; env_coef = 1;                                           // :1019-1021
+    } else {
+        gen_coef = sqrt(hsq / pheno_var);                                     // :1023
+        env_coef = sqrt(1.0 - hsq);                                           // :1024
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && coef) { coef[0] = gen_coef; coef[1] = env_coef; }
+#pragma unroll
+    for (int u = 0; u < kHerKeep; u++) {
+        const int64_t i = lo + (int64_t)u * kHerThreads + threadIdx.x;
+        if (i < hi) y[i] = __dadd_rn(__dmul_rn(keep[u], gen_coef), __dmul_rn(noise[i], env_coef));      // :1027, no FMA contraction
+    }
+    for (int64_t i = lo + (int64_t)kHerKeep * kHerThreads + threadIdx.x; i < hi; i += kHerThreads)
+        y[i] = __dadd_rn(__dmul_rn(y[i], gen_coef), __dmul_rn(noise[i], env_coef));
+}
+
 // ------------------------------------------------------- effect-size scaling
 
 // Per causal variant (source.cc:1245-1262, :1272-1286, :1089-1094):
@@ -520,6 +569,26 @@ int launch_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, c
     heritability_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(hsq, d_y, n, d_noise, d_sumsq, d_coef);
     ctx->launches++;
     return ctx_cuda(ctx, cudaGetLastError(), "heritability launch");
+}
+
+int launch_apply_heritability(simu_b200_ctx *ctx, float hsq, double *d_y, int64_t n, const double *d_noise, double *d_coef)
+{
+    if (n <= 0) return ctx_fail(ctx, SIMU_B200_EINVAL, "heritability: n must be positive");
+    int64_t grid = (n + 4 * kHerThreads - 1) / (4 * kHerThreads);
+    const int64_t most = ctx->num_sms < kHerThreads ? ctx->num_sms : kHerThreads;      // co-resident, one partial per thread
+    if (grid > most) grid = most;
+    const bool fresh = ctx->scratch_bytes[SCR_HERIT] < 4096;
+    uint8_t *scr = (uint8_t *)ctx_scratch(ctx, SCR_HERIT, 4096);
+    if (!scr) return SIMU_B200_ENOMEM;
+    if (fresh) CUDA_TRY(ctx, cudaMemsetAsync(scr, 0, 4096, ctx->stream));      // the barrier counters: the kernel leaves them zero
+    unsigned int *bar = (unsigned int *)scr;
+    double *partial = (double *)(scr + 64);
+    void *args[] = {(void *)&hsq, (void *)&d_y, (void *)&n, (void *)&d_noise, (void *)&partial, (void *)&bar, (void *)&d_coef};
+    const int ps = prof_begin(ctx, PROF_REDUCTIONS);
+    cudaError_t e = cudaLaunchCooperativeKernel((void *)heritability_fused_kernel, dim3((unsigned)grid), dim3(kHerThreads), args, 0, ctx->stream);
+    prof_end(ctx, ps);
+    ctx->launches++;
+    return ctx_cuda(ctx, e, "heritability_fused_kernel launch");
 }
 
 int launch_scale_effects_on(simu_b200_ctx *ctx, cudaStream_t stream, const double *d_freq, double *d_x1, double *d_x2,

@@ -369,6 +369,35 @@ def test_apply_heritability_parity():
         assert (gen, env) == (0.0, 1.0) and np.array_equal(gy, noise)
 
 
+@pytest.mark.parametrize("n", [1, 31, 1024, 1025, 12345, 151_553, 1_000_003])
+def test_apply_heritability_device_forms(n):
+    """simu_b200_apply_heritability_dev (one cooperative launch: per-block sums, grid barrier, scaling) against the
+    oracle and against simu_b200_sumsq_dev + simu_b200_heritability_dev, twice in a row (the barrier resets itself)."""
+    import torch
+    rng = np.random.default_rng(n)
+    y = rng.standard_normal(n) * 3.0
+    noise = rng.standard_normal(n)
+    hsq = float(np.float32(0.37))
+    oy, _, ogen, oenv = oracle.apply_heritability(hsq, y, noise, None)
+    with capi.Context(n) as ctx:
+        d_noise = torch.from_numpy(noise).cuda()
+        d_coef = torch.zeros(4, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            d_y = torch.from_numpy(y).cuda()
+            torch.cuda.synchronize()
+            ctx.apply_heritability_dev(hsq, d_y.data_ptr(), n, d_noise.data_ptr(), d_coef.data_ptr())
+            ctx.sync()
+            gy, coef = d_y.cpu().numpy(), d_coef.cpu().numpy()
+            assert coef[1] == oenv and abs(coef[0] - ogen) <= 1e-12 * abs(ogen)
+            assert np.max(np.abs(gy - oy)) <= 1e-12 * np.max(np.abs(oy))
+        d_y2 = torch.from_numpy(y).cuda()
+        torch.cuda.synchronize()
+        ctx.sumsq_dev(d_y2.data_ptr(), n, d_coef[2:].data_ptr())
+        ctx.heritability_dev(hsq, d_y2.data_ptr(), n, d_noise.data_ptr(), d_coef[2:].data_ptr(), 0)
+        ctx.sync()
+        assert np.max(np.abs(d_y2.cpu().numpy() - gy)) <= 1e-12 * np.max(np.abs(oy))
+
+
 def test_scale_effects_parity():
     """het^S / sqrt(het) effect scaling (source.cc:1245-1262, :1272-1286, :1089-1094) on the device:
     sqrt and division are correctly rounded -> ops 1, 2 bit-exact; pow -> 1e-14."""
