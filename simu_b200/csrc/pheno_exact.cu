@@ -14,7 +14,8 @@
 // never be -0.0 (it starts at +0.0, and x + (-x) rounds to +0.0).
 //
 // This mode is FP64-pipe / shared-memory bound, not HBM bound; it is the
-// parity anchor.  The FAST mode (pheno_lut.cu) is the throughput path.
+// parity anchor and the CLI's default.  The FAST mode (pheno_tc.cu, pheno_lut.cu)
+// is the throughput path.  The SAMPLE16 kernels (the product layout) are at the end.
 #include <stdlib.h>
 #include <string.h>
 
@@ -252,91 +253,26 @@ pheno_exact_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, in
 }
 
 
-// SAMPLE16, second form: the EFFECTS come from the kernel-parameter constant bank.
+// SAMPLE16, second form (the default): the EFFECTS come from the kernel-parameter constant bank, TWO samples per thread.
 //
 // The kernel above gathers the finished addend (a - 2f) x_k per trait: 16 bytes per sample and SNP for two
 // traits through the 128 B/clk shared-memory pipe -- 2e10 gathers are 4.4 ms on config 2 whatever else happens
 // (measured 7.4 ms).  Here the table holds only t = a - 2f (8 bytes, the same for both traits) and the
 // multiplication by x_k is done per sample with x_k as a CONSTANT-BANK operand: a warp-uniform value costs no
-// shared-memory or register-file bandwidth there.  The arithmetic is the reference's, operation for operation
-// (source.cc:986-996: `(a - avg) * x` then `+=`): __dsub_rn once per SNP, __dmul_rn and __dadd_rn per sample --
-// bit-identical.  A missing genotype has t = +0.0: the product is +-0.0 and adding it leaves the accumulator
-// unchanged (it can never be -0.0), which equals the reference's `continue` for finite effects.
-// The effects of kParamSnps SNPs travel as a __grid_constant__ kernel parameter (24 KB of the 32 KB limit), so
+// shared-memory or register-file bandwidth there (SASS: LDCU.64 + DMUL R, R, UR).  The arithmetic is the reference's,
+// operation for operation (source.cc:986-996: `(a - avg) * x` then `+=`): __dsub_rn once per SNP, __dmul_rn and
+// __dadd_rn per sample -- bit-identical.  A missing genotype has t = +0.0: the product is +-0.0 and adding it leaves
+// the accumulator unchanged (it can never be -0.0), which equals the reference's `continue` for finite effects.
+// The effects of a slice of SNPs travel as a __grid_constant__ kernel parameter (24 KB of the 32 KB limit), so
 // a call is a chain of launches, each continuing every sample's sum from y (stream order keeps the SNP order).
-constexpr int kParamSnps = 1536;
-struct ExactEffects { double x[2][kParamSnps]; };
-constexpr int kThreadsP = 64;       // 1563 blocks for 100K samples: 10.6 per SM, so the uneven last block costs 4 %, not 14 %
-
-template <int K>
-__global__ void __launch_bounds__(kThreadsP)
-pheno_exact_s16p_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, int mc, int64_t n_samples,
-                        const double *__restrict__ freq, double *__restrict__ y1, double *__restrict__ y2, int accumulate,
-                        const __grid_constant__ ExactEffects eff)
-{
-    __shared__ __align__(16) double tbl[kChunk][4];           // [snp][dosage code] -> a - 2f, missing -> +0.0
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < n_samples;
-    const uint32_t *base = reinterpret_cast<const uint32_t *>(panel) + (active ? i : 0);
-    const int64_t gw = s16_stride >> 2;                        // words per group
-    double acc[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) acc[k] = (accumulate && active) ? (k == 0 ? y1[i] : y2[i]) : 0.0;
-
-    uint32_t w[4], wn[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) w[q] = (16 * q < mc) ? __ldg(base + q * gw) : 0u;
-    for (int j0 = 0; j0 < mc; j0 += kChunk) {
-        const int nj = min(kChunk, mc - j0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < nj; t += blockDim.x) {
-            const double avg = __dmul_rn(2.0, freq[j0 + t]);     // source.cc:986
-            *reinterpret_cast<double2 *>(&tbl[t][0]) = make_double2(__dsub_rn(2.0, avg), __dsub_rn(1.0, avg));
-            *reinterpret_cast<double2 *>(&tbl[t][2]) = make_double2(__dsub_rn(0.0, avg), 0.0);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) wn[q] = (j0 + kChunk + 16 * q < mc) ? __ldg(base + ((j0 + kChunk) / 16 + q) * gw) : 0u;
-        __syncthreads();
-        const char *tb = reinterpret_cast<const char *>(&tbl[0][0]);
-        if (nj == kChunk) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-#pragma unroll
-                for (int f = 0; f < 16; f++) {
-                    const int jj = 16 * q + f;
-                    // byte offset of the table entry: the 2-bit code times 8
-                    const uint32_t off = (f == 0) ? (w[q] << 3) & 24u : (f == 1) ? (w[q] << 1) & 24u : (w[q] >> (2 * f - 3)) & 24u;
-                    const double t = *reinterpret_cast<const double *>(tb + jj * 32 + off);
-#pragma unroll
-                    for (int k = 0; k < K; k++) acc[k] = __dadd_rn(acc[k], __dmul_rn(t, eff.x[k][j0 + jj]));   // source.cc:994-995
-                }
-            }
-        } else {
-            for (int jj = 0; jj < nj; jj++) {
-                const uint32_t off = ((w[jj >> 4] >> (2 * (jj & 15))) & 3u) * 8u;
-                const double t = *reinterpret_cast<const double *>(tb + jj * 32 + off);
-#pragma unroll
-                for (int k = 0; k < K; k++) acc[k] = __dadd_rn(acc[k], __dmul_rn(t, eff.x[k][j0 + jj]));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) w[q] = wn[q];
-    }
-    if (active) {
-        y1[i] = acc[0];
-        if (K == 2) y2[i] = acc[K - 1];
-    }
-}
-
-// SAMPLE16, third form (the default): TWO samples per thread, one warp per block, effects interleaved by trait.
 //
-// ncu on the kernel above (profiles/r02f_exact_s16p_ncu.txt): 10.8 issued instructions per 32 samples and SNP at
-// 71 % of the issue slots, FP64 pipe 51 %, shared-memory pipe 52 % -- issue-bound before either data pipe.  Per 64
-// samples and SNP this form issues 2 LDS.64 + 2 (SHF + LOP3) + ONE LDCU.128 (both traits' effects) + 4 DMUL + 4 DADD:
+// ncu on the first version of this form (one sample per thread, 64-thread blocks; profiles/r02f_exact_s16p_ncu.txt):
+// 10.8 issued instructions per 32 samples and SNP at 71 % of the issue slots, FP64 pipe 51 %, shared-memory pipe 52 % -- issue-bound before either data pipe.  Per 64
+// samples and SNP this form issues 2 LDS.64 + 2 (SHF + LOP3) + 2 LDCU.64 (the traits' effects, adjacent in the parameter) + 4 DMUL + 4 DADD:
 // the uniform loads, the loop bookkeeping and the table build are shared by twice the samples, and a warp carries
 // four independent addition chains instead of two.  Same operations in the same order per sample -> same bits.
 // One warp per block keeps the block count at N/64 (1563 for 100K samples = 10.6 per SM; 64-thread blocks of two
-// samples per thread would be 5.3 per SM, a 14 % tail) (the kernel is compiled for up to 64 threads).
+// samples per thread would be 5.3 per SM, a 14 % tail).
 template <int K> struct alignas(16) ExactEffectsI { static constexpr int kSnps = (K == 2) ? 1536 : 3072; double x[kSnps][K]; };
 
 template <int K>
@@ -548,31 +484,10 @@ int launch_pheno_exact_s16(simu_b200_ctx *ctx, int64_t mc, const double *d_freq,
         hx1 = ctx->h_eff; hx2 = k2 ? ctx->h_eff + mc : nullptr;
     }
     const int ps = prof_begin(ctx, PROF_PHENO_EXACT);
-    static const bool one_sample = getenv("SIMU_B200_EXACT_V") && atoi(getenv("SIMU_B200_EXACT_V")) == 0;   // A/B runs: one sample per thread
-    if (param_kernel && !one_sample) {
+    if (param_kernel) {
         const int rc = k2 ? launch_exact_s16d<2>(ctx, mc, d_freq, hx1, hx2, d_y1, d_y2, accumulate)
                           : launch_exact_s16d<1>(ctx, mc, d_freq, hx1, nullptr, d_y1, nullptr, accumulate);
         if (rc) return rc;
-    } else if (param_kernel) {
-        const int64_t blocks = (ctx->n_samples + kThreadsP - 1) / kThreadsP;
-        std::unique_ptr<ExactEffects> effp(new (std::nothrow) ExactEffects);      // host staging of one launch's parameters
-        if (!effp) return ctx_fail(ctx, SIMU_B200_ENOMEM, "find_pheno: out of host memory");
-        ExactEffects &eff = *effp;
-        memset(&eff, 0, sizeof(eff));
-        for (int64_t j0 = 0; j0 < mc; j0 += kParamSnps) {
-            const int n = (int)std::min<int64_t>(kParamSnps, mc - j0);
-            memcpy(eff.x[0], hx1 + j0, (size_t)n * sizeof(double));
-            if (k2) memcpy(eff.x[1], hx2 + j0, (size_t)n * sizeof(double));
-            const uint8_t *panel = ctx->panel + (j0 / 16) * ctx->s16_stride;
-            const int acc = (accumulate || j0 > 0) ? 1 : 0;
-            if (k2)
-                pheno_exact_s16p_kernel<2><<<(unsigned)blocks, kThreadsP, 0, ctx->stream>>>(panel, ctx->s16_stride, n, ctx->n_samples,
-                                                                                         d_freq + j0, d_y1, d_y2, acc, eff);
-            else
-                pheno_exact_s16p_kernel<1><<<(unsigned)blocks, kThreadsP, 0, ctx->stream>>>(panel, ctx->s16_stride, n, ctx->n_samples,
-                                                                                         d_freq + j0, d_y1, nullptr, acc, eff);
-            ctx->launches++;
-        }
     } else {
         const int64_t blocks = (ctx->n_samples + kThreads - 1) / kThreads;
         if (k2)
