@@ -252,7 +252,7 @@ def _roofline(kernel, alg_bytes_per_launch, ms, n_launches, peaks, peak_src, tra
 
 
 KERNEL_NAMES = {  # layout -> (counts kernel, FAST kernel, EXACT kernel)
-    "s16": ("counts_s16_kernel", "pheno_tc_kernel", "pheno_exact_s16_kernel"),
+    "s16": ("counts_s16_kernel", "pheno_tc_kernel", "pheno_exact_s16d_kernel"),
     "group4": ("counts_g4_kernel", "pheno_lut_g4_kernel", "pheno_exact_g4_kernel"),
     "rows": ("counts_kernel", "pheno_lut_kernel", "pheno_exact_kernel"),
 }
