@@ -163,7 +163,7 @@ constexpr uint32_t kIdesc = (2u << 4) | (0u << 7) | (1u << 10) | ((16u >> 3) << 
 
 // ------------------------------------------------------------------ weights
 
-struct TcScale {            // per trait, written by tc_prepare_kernel
+struct TcScale {            // per trait, written by the weight kernels
     double constant;        // C = sum_j x_j (2 - 2 f_j)
     int exponent;           // e: weights are integers in units of 2^e
     int pad;
@@ -176,70 +176,7 @@ __device__ __forceinline__ void weights_of(double f, double x, double &wp, doubl
     c = x * (2.0 - 2.0 * f);
 }
 
-constexpr int kPrepBlocks = 128, kPrepThreads = 256;
-
-// pass 1: largest |W| per trait (-> the power-of-two quantum) and the constant term, summed in a fixed order
-template <int K>
-__global__ void __launch_bounds__(kPrepThreads)
-tc_prepare_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
-                  double *__restrict__ partial /* [K][kPrepBlocks] sums, then [K][kPrepBlocks] maxima */,
-                  unsigned int *__restrict__ ticket, TcScale *__restrict__ scale)
-{
-    __shared__ double ssum[K][kPrepThreads], smax[K][kPrepThreads];
-    __shared__ bool last;
-    double sum[K], mx[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) { sum[k] = 0.0; mx[k] = 0.0; }
-    for (int64_t j = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x; j < mc; j += (int64_t)kPrepBlocks * kPrepThreads) {
-        const double f = freq[j];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            double wp, wm, c;
-            weights_of(f, k == 0 ? x1[j] : x2[j], wp, wm, c);
-            sum[k] += c;
-            mx[k] = fmax(mx[k], fmax(fabs(wp), fabs(wm)));
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) { ssum[k][threadIdx.x] = sum[k]; smax[k][threadIdx.x] = mx[k]; }
-    __syncthreads();
-    for (int s = kPrepThreads / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                ssum[k][threadIdx.x] += ssum[k][threadIdx.x + s];
-                smax[k][threadIdx.x] = fmax(smax[k][threadIdx.x], smax[k][threadIdx.x + s]);
-            }
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            partial[k * kPrepBlocks + blockIdx.x] = ssum[k][0];
-            partial[(K + k) * kPrepBlocks + blockIdx.x] = smax[k][0];
-        }
-        __threadfence();
-        last = atomicAdd(ticket, 1u) == (unsigned)kPrepBlocks - 1u;
-    }
-    __syncthreads();
-    if (last && threadIdx.x < K) {
-        __threadfence();
-        const int k = threadIdx.x;
-        double s = 0.0, m = 0.0;
-        for (int b = 0; b < kPrepBlocks; b++) {
-            s += ((volatile double *)partial)[k * kPrepBlocks + b];
-            m = fmax(m, ((volatile double *)partial)[(K + k) * kPrepBlocks + b]);
-        }
-        scale[k].constant = s;
-        // |W| < 2^(ilogb(m) + 1)  ->  |W| / 2^e < 2^kFracBits
-        scale[k].exponent = (m > 0.0 && isfinite(m)) ? ilogb(m) + 1 - kFracBits : 0;
-        scale[k].pad = 0;
-        if (k == 0) *ticket = 0;
-    }
-}
-
-// pass 2: the weight tiles.  One work item (blk, t), t < 8 * K, converts the 16 SNPs of one (64-SNP block, group q,
+// the weight tiles.  One work item (blk, t), t < 8 * K, converts the 16 SNPs of one (64-SNP block, group q,
 // plane, trait) to fixed point ONCE and writes all eight digit columns of that trait (128 bytes).
 template <int K>
 __device__ __forceinline__ void weight_item(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2,
@@ -295,20 +232,11 @@ __device__ __forceinline__ void weight_item(const double *__restrict__ freq, con
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(128)
-tc_weights_kernel(const double *__restrict__ freq, const double *__restrict__ x1, const double *__restrict__ x2, int64_t mc,
-                  int64_t ntiles, const TcScale *__restrict__ scale, uint8_t *__restrict__ wt, long long *__restrict__ wm_fix)
-{
-    const double inv_quantum[2] = {ldexp(1.0, -scale[0].exponent), K == 2 ? ldexp(1.0, -scale[1].exponent) : 0.0};
-    const int64_t item = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (item < ntiles * (8 * K)) weight_item<K>(freq, x1, x2, mc, inv_quantum, wt, item / (8 * K), (int)(item % (8 * K)), wm_fix);
-}
-
-// both passes in ONE cooperative launch (default above kSmallMc): every block sums / maximises its strided share, the blocks
+// Pass 1 (largest |W| per trait -> the power-of-two quantum; the constant term, summed in a fixed order) and pass 2 (the
+// tiles) in ONE cooperative launch (causal sets above kSmallMc): every block sums / maximises its strided share, the blocks
 // meet at a grid barrier, EVERY block reduces the per-block partials in the same fixed order (so all of them hold the same
-// exponents without another round trip) and goes on to its share of the weight tiles.  Replaces memset + tc_prepare_kernel
-// + tc_weights_kernel (29 us of a 0.81 ms step on config 2, 28 us of 0.17 ms on config 3: two launches, a serial
+// exponents without another round trip) and goes on to its share of the weight tiles.  It replaced memset + a prepare kernel
+// + a weights kernel (29 us of a 0.81 ms step on config 2, 28 us of 0.17 ms on config 3: two launches, a serial
 // last-block loop over 128 partials and a ticket).  The barrier cleans up after itself: the last block to leave zeroes both
 // counters, so the launch parameters never change and the step still replays as one CUDA graph.
 constexpr int kFusedThreads = 256;
@@ -765,19 +693,16 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
         if (miss_correct_accumulates(ctx)) CUDA_TRY(ctx, cudaMemsetAsync(corr, 0, corr_bytes, ctx->stream));
     }
 
-    // weight tiles, then: [TcScale x 2][ticket + pad][partials 4 x kPrepBlocks doubles]
+    // weight tiles, then: [TcScale x 2][pad][partials 4 x kFusedThreads doubles]
     const size_t wt_bytes = (size_t)nblocks * kHalves * kWTileBytes;
     const size_t aux_off = (wt_bytes + 255) & ~(size_t)255;
-    static_assert(kFusedThreads >= kPrepBlocks, "partials");
     uint8_t *wt = (uint8_t *)ctx_scratch(ctx, SCR_TCW, aux_off + 64 + 4 * kFusedThreads * sizeof(double));
     const size_t ypart_bytes = (size_t)slots * K * npad * sizeof(double);
     double *ypart = (double *)ctx_scratch(ctx, SCR_YPART, ypart_bytes);
     if (!wt || !ypart) return SIMU_B200_ENOMEM;
     TcScale *scale = reinterpret_cast<TcScale *>(wt + aux_off);
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(wt + aux_off + 32);
     double *partial = reinterpret_cast<double *>(wt + aux_off + 64);
     // the fused weight kernel's barrier counters: zero between launches (the kernel resets them), cleared when first allocated
-    static const bool use_fused = getenv("SIMU_B200_TC_WEIGHTS_SPLIT") == nullptr;     // A/B runs: the two-kernel form
     const bool fbar_fresh = ctx->scratch_bytes[SCR_FUSED] < 64;
     unsigned int *fbar = (unsigned int *)ctx_scratch(ctx, SCR_FUSED, 64);
     if (!fbar) return SIMU_B200_ENOMEM;
@@ -796,7 +721,7 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
     int ps = prof_begin(ctx, PROF_LUT_BUILD);
     if (mc <= kSmallMc) {
         tc_small_prepare_kernel<K><<<1, kSmallThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt, wm_fix);
-    } else if (use_fused) {
+    } else {
         const int64_t items = nblocks * kHalves * 8 * K, most = items > mc ? items : mc;
         int64_t fgrid = (most + kFusedThreads - 1) / kFusedThreads;
         const int64_t fmax_grid = ctx->num_sms < kFusedThreads ? ctx->num_sms : kFusedThreads;     // co-resident, and one partial per thread
@@ -807,12 +732,6 @@ int run_tc(simu_b200_ctx *ctx, int64_t mc, const double *d_freq, const double *d
         void *args[] = {(void *)&a_freq, (void *)&a_x1, (void *)&a_x2, (void *)&a_mc, (void *)&ntiles, (void *)&partial,
                         (void *)&fbar, (void *)&scale, (void *)&wt, (void *)&wm_fix};
         CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void *)tc_weights_fused_kernel<K>, dim3((unsigned)fgrid), dim3(kFusedThreads), args, 0, ctx->stream));
-    } else {
-        CUDA_TRY(ctx, cudaMemsetAsync(ticket, 0, 32, ctx->stream));
-        tc_prepare_kernel<K><<<kPrepBlocks, kPrepThreads, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, partial, ticket, scale);
-        const int64_t items = nblocks * kHalves * 8 * K;
-        tc_weights_kernel<K><<<(unsigned)((items + 127) / 128), 128, 0, ctx->stream>>>(d_freq, d_x1, d_x2, mc, nblocks * kHalves, scale, wt, wm_fix);
-        ctx->launches++;
     }
     prof_end(ctx, ps);
 
