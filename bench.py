@@ -450,6 +450,9 @@ class Workload:
             # use) with the correction pass beside the main kernel, or as a dense plane of the MMA (include/simu_b200.h)
             "missing_genotypes": {1: f"sparse index, {miss_entries} entries", 2: "dense MMA plane", 0: "dense MMA plane (index not built)"}[miss_state],
         }
+        if not fast and out["roofline"]:      # the ordered FP64 kernel is not an HBM kernel: say so next to the HBM fraction
+            out["roofline"]["note"] = ("EXACT mode is bound by issue slots, the FP64 pipe and the shared-memory gather together "
+                                       "(DESIGN.md 3 b1), not by HBM; the HBM fraction is reported for comparison with FAST only")
         return out
 
     def close(self):
