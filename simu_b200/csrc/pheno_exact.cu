@@ -345,7 +345,7 @@ pheno_exact_s16d_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, i
                     const double t0 = *reinterpret_cast<const double *>(tb + jj * 32 + o0);
                     const double t1 = *reinterpret_cast<const double *>(tb + jj * 32 + o1);
                     double x[2];
-                    if (K == 2) *reinterpret_cast<double2 *>(x) = *reinterpret_cast<const double2 *>(&eff.x[j0 + jj][0]);   // one LDCU.128
+                    if (K == 2) *reinterpret_cast<double2 *>(x) = *reinterpret_cast<const double2 *>(&eff.x[j0 + jj][0]);   // adjacent in the parameter (ptxas: two LDCU.64)
                     else x[0] = eff.x[j0 + jj][0];
 #pragma unroll
                     for (int k = 0; k < K; k++) {
