@@ -257,6 +257,7 @@ struct S16Tma {
     int64_t ngroups;
     int cpg;                    // chunks per group
     int64_t total;              // ngroups * cpg
+    int spread;                 // range -> warp assignment (see the kernel)
 };
 
 __device__ __forceinline__ int64_t warp_of_chunk(int64_t x, int64_t warps, int64_t total) { return ((x + 1) * warps - 1) / total; }
@@ -270,7 +271,12 @@ counts_s16_tma_kernel(const S16Tma p)
     // participating warps: never more than chunks, so that no range is empty (the ticket of a straddling group counts
     // the warps between its first and its last owner)
     const int64_t launched = (int64_t)gridDim.x * kWarpsT, warps = launched < p.total ? launched : p.total;
-    const int64_t me = (int64_t)blockIdx.x * kWarpsT + warp;
+    // which contiguous range this warp takes: ranges that are neighbours in the panel go to DIFFERENT SMs (an SM's eight
+    // warps read eight regions spread over the panel instead of one 17 MB run).  ncu, config 2, active cycles per SM
+    // min / avg / max: 599K / 665K / 755K with neighbouring ranges on one SM, 610K / 664K / 721K spread (the kernel ends
+    // with its slowest warp: 397 -> 383 us, config 5 1.94 -> 1.87 ms, config 3 58.6 -> 55.0 us on the same box).  The rest
+    // of the spread is per-warp: every warp streams a fixed share through its own ring.
+    const int64_t me = p.spread ? (int64_t)warp * gridDim.x + blockIdx.x : (int64_t)blockIdx.x * kWarpsT + warp;
     const int64_t c_begin = me < warps ? (me * p.total) / warps : 0, c_end = me < warps ? ((me + 1) * p.total) / warps : 0;
     const uint32_t ring = smem_addr(smem) + (uint32_t)(warp * kRing * kSlotBytes);
     const uint32_t bars = smem_addr(smem) + (uint32_t)(kWarpsT * kRing * kSlotBytes + warp * kRing * 8);
@@ -405,6 +411,7 @@ static int launch_counts_s16_tma(simu_b200_ctx *ctx, cudaStream_t stream, int64_
     p.ngroups = (mc + 15) >> 4;
     p.cpg = (int)((ctx->s16_stride + kSlotBytes - 1) / kSlotBytes);
     p.total = p.ngroups * p.cpg;
+    { const char *e = getenv("SIMU_B200_COUNTS_SPREAD"); p.spread = e ? atoi(e) : 1; }
     // partial sums of the groups that straddle two warps' ranges + their tickets: zero between calls (the finalising
     // warp clears what it reads), so only a new or larger buffer is cleared here
     const size_t acc_bytes = (size_t)p.ngroups * 49 * sizeof(unsigned int);
