@@ -275,7 +275,7 @@ counts_s16_tma_kernel(const S16Tma p)
     // warps read eight regions spread over the panel instead of one 17 MB run).  ncu, config 2, active cycles per SM
     // min / avg / max: 599K / 665K / 755K with neighbouring ranges on one SM, 610K / 664K / 721K spread (the kernel ends
     // with its slowest warp: 397 -> 383 us, config 5 1.94 -> 1.87 ms, config 3 58.6 -> 55.0 us on the same box).  The rest
-    // of the spread is per-warp: every warp streams a fixed share through its own ring.
+    // of the spread is per-warp; a dynamic tail that balances it was measured and does not shorten the kernel.
     const int64_t me = p.spread ? (int64_t)warp * gridDim.x + blockIdx.x : (int64_t)blockIdx.x * kWarpsT + warp;
     const int64_t c_begin = me < warps ? (me * p.total) / warps : 0, c_end = me < warps ? ((me + 1) * p.total) / warps : 0;
     const uint32_t ring = smem_addr(smem) + (uint32_t)(warp * kRing * kSlotBytes);
