@@ -268,7 +268,9 @@ pheno_exact_s16_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, in
 //
 // ncu on the first version of this form (one sample per thread, 64-thread blocks; profiles/r02f_exact_s16p_ncu.txt):
 // 10.8 issued instructions per 32 samples and SNP at 71 % of the issue slots, FP64 pipe 51 %, shared-memory pipe 52 % -- issue-bound before either data pipe.  Per 64
-// samples and SNP this form issues 2 LDS.64 + 2 (SHF + LOP3) + 2 LDCU.64 (the traits' effects, adjacent in the parameter) + 4 DMUL + 4 DADD:
+// samples and SNP this form issues 2 LDS.64 + 2 PRMT (the table offsets: the codes of a word are multiplied by 8 four fields
+// at a time, 8 shifts + 8 LOP3 per 16 SNPs, and a byte permute picks one -- 3.98 -> 3.81 ms against a shift + mask per SNP)
+// + 2 LDCU.64 (the traits' effects, adjacent in the parameter) + 4 DMUL + 4 DADD:
 // the uniform loads, the loop bookkeeping and the table build are shared by twice the samples, and a warp carries
 // four independent addition chains instead of two.  Same operations in the same order per sample -> same bits.
 // One warp per block keeps the block count at N/64 (1563 for 100K samples = 10.6 per SM; 64-thread blocks of two
@@ -336,12 +338,15 @@ pheno_exact_s16d_kernel(const uint8_t *__restrict__ panel, int64_t s16_stride, i
         if (nj == kChunk) {
 #pragma unroll
             for (int q = 0; q < 4; q++) {
+                // the codes times 8, four fields per word: byte b of u[k] is the table offset of SNP 4b + k
+                const uint32_t u0[4] = {(w[q].x << 3) & 0x18181818u, (w[q].x << 1) & 0x18181818u, (w[q].x >> 1) & 0x18181818u, (w[q].x >> 3) & 0x18181818u};
+                const uint32_t u1[4] = {(w[q].y << 3) & 0x18181818u, (w[q].y << 1) & 0x18181818u, (w[q].y >> 1) & 0x18181818u, (w[q].y >> 3) & 0x18181818u};
 #pragma unroll
                 for (int f = 0; f < 16; f++) {
                     const int jj = 16 * q + f;
                     // byte offset of the table entry: the 2-bit code times 8
-                    const uint32_t o0 = (f == 0) ? (w[q].x << 3) & 24u : (f == 1) ? (w[q].x << 1) & 24u : (w[q].x >> (2 * f - 3)) & 24u;
-                    const uint32_t o1 = (f == 0) ? (w[q].y << 3) & 24u : (f == 1) ? (w[q].y << 1) & 24u : (w[q].y >> (2 * f - 3)) & 24u;
+                    const uint32_t o0 = __byte_perm(u0[f & 3], 0u, 0x4440u + (f >> 2));
+                    const uint32_t o1 = __byte_perm(u1[f & 3], 0u, 0x4440u + (f >> 2));
                     const double t0 = *reinterpret_cast<const double *>(tb + jj * 32 + o0);
                     const double t1 = *reinterpret_cast<const double *>(tb + jj * 32 + o1);
                     double x[2];
